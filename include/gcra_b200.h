@@ -1,0 +1,188 @@
+/*
+ * gcra_b200.h -- C ABI of the B200-native batched GCRA rate-limit engine.
+ *
+ * This is the drop-in boundary for ONE path of lazureykis/throttlecrab: the GCRA
+ * decide-and-update behind `RateLimiter::rate_limit` over a `Store`, plus the
+ * expired-key sweep.  Every entry point names the reference interface it replaces
+ * (paths relative to the reference checkout).  Plain pointers and sizes only; no
+ * torch / CUDA types in any signature (a `void *stream` is a cudaStream_t, NULL =
+ * the engine's own stream).  A handle is single-owner, like the reference's
+ * `&mut self` stores (core/store/mod.rs:40-43): no internal locking.
+ *
+ * The engine never falls back to the CPU: gcra_create fails (GCRA_INTERNAL) when
+ * no CUDA device is usable.
+ */
+#ifndef GCRA_B200_H
+#define GCRA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Status codes mirror CellError (core/mod.rs:48-56). */
+enum {
+    GCRA_OK = 0,
+    GCRA_NEGATIVE_QUANTITY = 1,  /* CellError::NegativeQuantity  rate_limiter.rs:111-113 */
+    GCRA_INVALID_RATE_LIMIT = 2, /* CellError::InvalidRateLimit  rate_limiter.rs:115-117 */
+    GCRA_INTERNAL = 3            /* CellError::Internal(String); see gcra_last_error()   */
+};
+
+/* Sweep policy = which reference store the table stands in for. */
+enum {
+    GCRA_STORE_PERIODIC = 0,      /* PeriodicStore       periodic.rs:128-142        p0 = interval s (0 -> 60)        */
+    GCRA_STORE_PROBABILISTIC = 1, /* ProbabilisticStore  probabilistic.rs:110-125   p0 = modulo (0 -> 1000)          */
+    GCRA_STORE_ADAPTIVE = 2,      /* AdaptiveStore       adaptive_cleanup.rs:138-211 p0/p1 = min/max s, p2 = max ops */
+    GCRA_STORE_MANUAL = 3         /* never sweeps on its own; call gcra_sweep()                                     */
+};
+
+typedef struct gcra_engine gcra_engine;
+
+typedef struct {
+    uint64_t capacity;    /* expected live keys, like Store::with_capacity (adaptive_cleanup.rs:91-104) */
+    int32_t device;       /* CUDA ordinal */
+    int32_t store_kind;   /* GCRA_STORE_* */
+    uint64_t p0, p1, p2;  /* policy parameters, 0 = the reference's library default */
+    int64_t created_ns;   /* stands in for SystemTime::now() in the constructors (adaptive_cleanup.rs:94) */
+    uint32_t max_batch;   /* largest number of requests one kernel pass carries (0 -> 1<<20) */
+    uint32_t flags;       /* reserved, 0 */
+} gcra_config;
+
+/* One call of RateLimiter::rate_limit(key, max_burst, count_per_period, period, quantity, now)
+ * (rate_limiter.rs:102-110), the key replaced by its 64-bit hash. 48 bytes. */
+typedef struct {
+    uint64_t key_hash;
+    int64_t max_burst;
+    int64_t count_per_period;
+    int64_t period;           /* seconds */
+    int64_t quantity;
+    int64_t now_ns;           /* now.duration_since(UNIX_EPOCH).as_nanos() as i64 (rate_limiter.rs:126-127) */
+} gcra_request;
+
+/* (bool, RateLimitResult) (rate_limiter.rs:12-22); `limit` is the request's max_burst. 32 bytes. */
+typedef struct {
+    int64_t remaining;
+    int64_t reset_after_ns;
+    int64_t retry_after_ns;
+    int32_t status;           /* GCRA_OK or the CellError the reference returns for this request */
+    uint8_t allowed;
+    uint8_t pad[3];
+} gcra_result;
+
+/* Compact request for the policy-table path: 16 bytes over PCIe instead of 48.
+ * policy = index into the table registered with gcra_set_policies(); `now` is per call. */
+typedef struct {
+    uint64_t key_hash;
+    int32_t quantity;
+    uint32_t policy;
+} gcra_request16;
+
+typedef struct {
+    int64_t max_burst, count_per_period, period;
+} gcra_policy;
+
+typedef struct {
+    uint64_t len;             /* entries holding state, like HashMap::len() (periodic.rs:113-116) */
+    uint64_t occupied_slots;  /* claimed table slots (len + keys seen only by denied requests) */
+    uint64_t table_slots;
+    uint64_t stash_entries;
+    uint64_t allowed, denied, errors;   /* totals since creation */
+    uint64_t expired_hits;    /* writes that replaced an expired entry (adaptive_cleanup.rs:233,267) */
+    uint64_t sweeps, swept;   /* sweep launches / entries removed */
+    uint64_t grows;
+} gcra_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+/* AdaptiveStore::with_capacity / builders (adaptive_cleanup.rs:91-136, periodic.rs:84-111) */
+int32_t gcra_create(const gcra_config *cfg, gcra_engine **out);
+void gcra_destroy(gcra_engine *h);
+/* text of the last GCRA_INTERNAL on this handle (the String of CellError::Internal) */
+const char *gcra_last_error(gcra_engine *h);
+
+/* ---- host helpers (no device work) ---------------------------------------------------- */
+/* the key -> 64-bit identity the table stores instead of the String key (adaptive_cleanup.rs:40) */
+uint64_t gcra_hash_key(const void *key, uint64_t len);
+/* hash n keys of the form "<prefix><decimal id>" (trace generation: "k:<i>") */
+void gcra_hash_key_ids(const void *prefix, uint64_t prefix_len, const uint64_t *ids, uint64_t n,
+                       uint64_t *out);
+/* Rate::from_count_and_period(..).period() and the dvt product, in i64 ns
+ * (rate/mod.rs:164-176, rate_limiter.rs:120-122,154-155).  GCRA_INTERNAL where the reference panics. */
+int32_t gcra_derive_params(int64_t max_burst, int64_t count_per_period, int64_t period,
+                           int64_t *emission_interval_ns, int64_t *tolerance_ns);
+
+/* ---- Store trait, one key at a time (core/store/mod.rs:85-133) ------------------------- */
+/* Store::get (adaptive_cleanup.rs:246-252) */
+int32_t gcra_store_get(gcra_engine *h, const void *key, uint64_t len, int64_t now_ns,
+                       int64_t *value, uint8_t *found);
+/* Store::compare_and_swap_with_ttl (adaptive_cleanup.rs:221-244) */
+int32_t gcra_store_cas(gcra_engine *h, const void *key, uint64_t len, int64_t old_value,
+                       int64_t new_value, uint64_t ttl_ns, int64_t now_ns, uint8_t *swapped);
+/* Store::set_if_not_exists_with_ttl (adaptive_cleanup.rs:254-278) */
+int32_t gcra_store_set_nx(gcra_engine *h, const void *key, uint64_t len, int64_t value,
+                          uint64_t ttl_ns, int64_t now_ns, uint8_t *stored);
+
+/* ---- RateLimiter::rate_limit ---------------------------------------------------------- */
+/* one decision (rate_limiter.rs:102-250); returns the status also written to out->status */
+int32_t gcra_rate_limit(gcra_engine *h, const void *key, uint64_t len, int64_t max_burst,
+                        int64_t count_per_period, int64_t period, int64_t quantity,
+                        int64_t now_ns, gcra_result *out);
+
+/* n decisions with results defined as if the requests were applied in index order -- what the
+ * server's actor loop does one message at a time (throttlecrab-server/src/actor.rs:217-236).
+ * Host buffers; copies in, runs the kernels, copies out, returns when `res` is filled. */
+int32_t gcra_rate_limit_batch(gcra_engine *h, uint64_t n, const gcra_request *req, gcra_result *res);
+/* same with device-resident buffers, asynchronous on `stream` (n <= max_batch) */
+int32_t gcra_rate_limit_batch_device(gcra_engine *h, uint64_t n, const gcra_request *d_req,
+                                     gcra_result *d_res, void *stream);
+
+/* compact requests: register the (max_burst, count, period) table once, then 16-byte requests */
+int32_t gcra_set_policies(gcra_engine *h, uint32_t n, const gcra_policy *policies);
+int32_t gcra_rate_limit_batch16(gcra_engine *h, uint64_t n, const gcra_request16 *req,
+                                int64_t now_ns, gcra_result *res);
+int32_t gcra_rate_limit_batch16_device(gcra_engine *h, uint64_t n, const gcra_request16 *d_req,
+                                       int64_t now_ns, gcra_result *d_res, void *stream);
+
+/* ---- pinned host ring: fill a slot in place, submit, collect ---------------------------- */
+/* replaces the actor's mpsc channel hand-off (actor.rs:68-82,217-236) for batched callers.
+ * Slots are processed strictly in submission order. compact != 0 -> slots hold gcra_request16. */
+int32_t gcra_ring_create(gcra_engine *h, uint32_t slots, uint32_t slot_capacity, int32_t compact);
+void *gcra_ring_requests(gcra_engine *h, uint32_t slot);        /* pinned, caller fills */
+gcra_result *gcra_ring_results(gcra_engine *h, uint32_t slot);  /* pinned, valid after wait */
+int32_t gcra_ring_submit(gcra_engine *h, uint32_t slot, uint32_t n, int64_t now_ns);
+int32_t gcra_ring_wait(gcra_engine *h, uint32_t slot);
+int32_t gcra_ring_poll(gcra_engine *h, uint32_t slot, int32_t *done);
+
+/* ---- sweep and introspection ------------------------------------------------------------ */
+/* HashMap::retain(expiry > now) (adaptive_cleanup.rs:176-182), unconditionally */
+int32_t gcra_sweep(gcra_engine *h, int64_t now_ns, uint64_t *removed);
+/* len() (periodic.rs:113-116) */
+uint64_t gcra_len(gcra_engine *h);
+int32_t gcra_get_stats(gcra_engine *h, gcra_stats *out);
+/* table entry of a key after the fact: returns found, tat and expiry (saturated to INT64_MAX) */
+int32_t gcra_peek(gcra_engine *h, uint64_t key_hash, int64_t *tat, int64_t *expiry_ns, uint8_t *found);
+/* block until all device work of this handle has finished */
+int32_t gcra_sync(gcra_engine *h);
+/* device time (ms) of the kernels of the most recent batch call, measured with CUDA events on
+ * the launching stream: [0] total, [1] ingest (hash probe), [2] sort, [3] decide */
+int32_t gcra_last_kernel_ms(gcra_engine *h, float out[4]);
+/* number of kernels this handle has launched since creation */
+uint64_t gcra_launch_count(gcra_engine *h);
+
+/* ---- multi-GPU routing (key space hash-sharded across engines, one per GPU) --------------- */
+/* owner shard of a key hash among n_shards */
+uint32_t gcra_owner_of(uint64_t key_hash, uint32_t n_shards);
+/* stable partition of a device-resident batch by owner shard: writes the requests grouped by
+ * owner (order inside a group = input order), per-owner counts, and for every output row its
+ * input index.  All pointers are device pointers except none; asynchronous on `stream`. */
+int32_t gcra_route_partition(gcra_engine *h, uint64_t n, const gcra_request *d_req,
+                             uint32_t n_shards, gcra_request *d_out, uint32_t *d_src_index,
+                             uint32_t *d_counts, void *stream);
+/* inverse: d_res_routed[i] belongs to input row d_src_index[i] */
+int32_t gcra_route_unpermute(gcra_engine *h, uint64_t n, const gcra_result *d_res_routed,
+                             const uint32_t *d_src_index, gcra_result *d_res, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,50 @@
+"""The CUDA table through the Store-shaped C ABI against the reference's Store contract and
+sweep tests (store_test_suite.rs, cleanup_test.rs)."""
+import pytest
+
+import throttlecrab_b200 as tc
+from store_contract import CONTRACT, NOW, S
+
+pytestmark = pytest.mark.gpu
+STORES = [tc.PeriodicStore, tc.ProbabilisticStore, tc.AdaptiveStore]
+
+
+@pytest.mark.parametrize("store_cls", STORES, ids=lambda c: c.__name__)
+@pytest.mark.parametrize("fn", CONTRACT, ids=lambda f: f.__name__)
+def test_store_contract(fn, store_cls):
+    st = store_cls(capacity=100, created_ns=NOW, max_batch=4096)
+    fn(st)
+    st.close()
+
+
+def test_cleanup_actually_happens():           # cleanup_test.rs:8-41 (also grows 100 -> 1000 keys)
+    st = tc.PeriodicStore(capacity=100, created_ns=NOW, max_batch=4096)
+    for i in range(1000):
+        st.set_if_not_exists_with_ttl("key_%d" % i, i, 1 * S, NOW)
+    assert st.len() == 1000
+    fut = NOW + 61 * S
+    st.set_if_not_exists_with_ttl("trigger", 999, 60 * S, fut)
+    assert st.len() < 50
+    assert st.get("trigger", fut) is not None
+    assert st.stats()["grows"] >= 1
+
+
+def test_cleanup_with_memory_pressure():       # cleanup_test.rs:44-83
+    st = tc.PeriodicStore(capacity=100, created_ns=NOW, max_batch=4096)
+    for i in range(500):
+        st.set_if_not_exists_with_ttl("key_%d" % i, i, (1 if i % 2 == 0 else 3600) * S, NOW)
+    later = NOW + 61 * S
+    st.set_if_not_exists_with_ttl("trigger", 999, 60 * S, later)
+    assert 200 < st.len() < 300
+    for i in range(1, 100, 2):
+        assert st.get("key_%d" % i, later) is not None
+
+
+def test_no_cleanup_without_triggers():        # cleanup_test.rs:86-107
+    st = tc.PeriodicStore(capacity=100, created_ns=NOW, max_batch=4096)
+    for i in range(100):
+        st.set_if_not_exists_with_ttl("key_%d" % i, i, 3600 * S, NOW)
+    for i in range(10):
+        st.get("key_%d" % i, NOW)
+    assert st.len() == 100
+    assert st.stats()["sweeps"] == 0

@@ -1,0 +1,114 @@
+"""Build and load libgcra_b200.so (the C ABI in include/gcra_b200.h) with ctypes.
+
+There is no CPU fallback: importing works anywhere (so the symbol table can be checked on a
+box without a GPU), but creating an engine fails loudly when the library or a CUDA device
+is missing.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+_SRC = os.path.join(_PKG, "csrc")
+SO_PATH = os.path.join(_PKG, "libgcra_b200.so")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "--shared", "-Xcompiler", "-fPIC"]
+
+REQ_DTYPE = np.dtype([("key_hash", "<u8"), ("max_burst", "<i8"), ("count_per_period", "<i8"),
+                      ("period", "<i8"), ("quantity", "<i8"), ("now_ns", "<i8")])
+RES_DTYPE = np.dtype([("remaining", "<i8"), ("reset_after_ns", "<i8"), ("retry_after_ns", "<i8"),
+                      ("status", "<i4"), ("allowed", "u1"), ("pad", "u1", (3,))])
+REQ16_DTYPE = np.dtype([("key_hash", "<u8"), ("quantity", "<i4"), ("policy", "<u4")])
+POLICY_DTYPE = np.dtype([("max_burst", "<i8"), ("count_per_period", "<i8"), ("period", "<i8")])
+assert REQ_DTYPE.itemsize == 48 and RES_DTYPE.itemsize == 32 and REQ16_DTYPE.itemsize == 16
+
+OK, NEGATIVE_QUANTITY, INVALID_RATE_LIMIT, INTERNAL = 0, 1, 2, 3
+STORE_PERIODIC, STORE_PROBABILISTIC, STORE_ADAPTIVE, STORE_MANUAL = 0, 1, 2, 3
+
+
+class Config(C.Structure):
+    _fields_ = [("capacity", C.c_uint64), ("device", C.c_int32), ("store_kind", C.c_int32),
+                ("p0", C.c_uint64), ("p1", C.c_uint64), ("p2", C.c_uint64),
+                ("created_ns", C.c_int64), ("max_batch", C.c_uint32), ("flags", C.c_uint32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in
+                ("len", "occupied_slots", "table_slots", "stash_entries", "allowed", "denied",
+                 "errors", "expired_hits", "sweeps", "swept", "grows")]
+
+
+def sources():
+    return [os.path.join(_SRC, f) for f in sorted(os.listdir(_SRC))] + \
+        [os.path.join(_ROOT, "include", "gcra_b200.h")]
+
+
+def build(force=False, verbose=False):
+    """nvcc cross-compiles for sm_100a without a GPU; the .so is kept in-tree."""
+    srcs = sources()
+    if not force and os.path.exists(SO_PATH) and all(
+            os.path.getmtime(s) <= os.path.getmtime(SO_PATH) for s in srcs):
+        return SO_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", SO_PATH, os.path.join(_SRC, "gcra_b200.cu")]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.check_call(cmd)
+    return SO_PATH
+
+
+# name -> (restype, argtypes); every symbol include/gcra_b200.h declares
+_vp, _u64, _i64, _u32, _i32 = C.c_void_p, C.c_uint64, C.c_int64, C.c_uint32, C.c_int32
+_pi64, _pu8, _pu64 = C.POINTER(C.c_int64), C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)
+SYMBOLS = {
+    "gcra_create": (_i32, [C.POINTER(Config), C.POINTER(_vp)]),
+    "gcra_destroy": (None, [_vp]),
+    "gcra_last_error": (C.c_char_p, [_vp]),
+    "gcra_hash_key": (_u64, [C.c_char_p, _u64]),
+    "gcra_hash_key_ids": (None, [C.c_char_p, _u64, _vp, _u64, _vp]),
+    "gcra_derive_params": (_i32, [_i64, _i64, _i64, _pi64, _pi64]),
+    "gcra_store_get": (_i32, [_vp, C.c_char_p, _u64, _i64, _pi64, _pu8]),
+    "gcra_store_cas": (_i32, [_vp, C.c_char_p, _u64, _i64, _i64, _u64, _i64, _pu8]),
+    "gcra_store_set_nx": (_i32, [_vp, C.c_char_p, _u64, _i64, _u64, _i64, _pu8]),
+    "gcra_rate_limit": (_i32, [_vp, C.c_char_p, _u64, _i64, _i64, _i64, _i64, _i64, _vp]),
+    "gcra_rate_limit_batch": (_i32, [_vp, _u64, _vp, _vp]),
+    "gcra_rate_limit_batch_device": (_i32, [_vp, _u64, _vp, _vp, _vp]),
+    "gcra_set_policies": (_i32, [_vp, _u32, _vp]),
+    "gcra_rate_limit_batch16": (_i32, [_vp, _u64, _vp, _i64, _vp]),
+    "gcra_rate_limit_batch16_device": (_i32, [_vp, _u64, _vp, _i64, _vp, _vp]),
+    "gcra_ring_create": (_i32, [_vp, _u32, _u32, _i32]),
+    "gcra_ring_requests": (_vp, [_vp, _u32]),
+    "gcra_ring_results": (_vp, [_vp, _u32]),
+    "gcra_ring_submit": (_i32, [_vp, _u32, _u32, _i64]),
+    "gcra_ring_wait": (_i32, [_vp, _u32]),
+    "gcra_ring_poll": (_i32, [_vp, _u32, C.POINTER(_i32)]),
+    "gcra_sweep": (_i32, [_vp, _i64, _pu64]),
+    "gcra_len": (_u64, [_vp]),
+    "gcra_get_stats": (_i32, [_vp, C.POINTER(Stats)]),
+    "gcra_peek": (_i32, [_vp, _u64, _pi64, _pi64, _pu8]),
+    "gcra_sync": (_i32, [_vp]),
+    "gcra_last_kernel_ms": (_i32, [_vp, C.POINTER(C.c_float * 4)]),
+    "gcra_launch_count": (_u64, [_vp]),
+    "gcra_owner_of": (_u32, [_u64, _u32]),
+    "gcra_route_partition": (_i32, [_vp, _u64, _vp, _u32, _vp, _vp, _vp, _vp]),
+    "gcra_route_unpermute": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            build()
+        L = C.CDLL(SO_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)      # AttributeError if the header and the library disagree
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib

@@ -1,0 +1,719 @@
+// gcra_b200.cu -- host side of the engine and the C ABI declared in include/gcra_b200.h.
+//
+// Host responsibilities: table allocation/growth (HashMap::with_capacity / growth), the sweep
+// policies of the three reference stores (adaptive_cleanup.rs:138-211, periodic.rs:128-142,
+// probabilistic.rs:110-125) driving the sweep kernel, kernel sequencing on CUDA streams, and the
+// pinned host ring.  All decisions are made by the kernels in gcra_kernels.cuh; there is no CPU
+// decision path.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gcra_kernels.cuh"
+
+using namespace gcra;
+
+#define CK(call)                                                                         \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess) {                                                         \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                 \
+            return GCRA_INTERNAL;                                                        \
+        }                                                                                \
+    } while (0)
+
+#define RC(call)                                  \
+    do {                                          \
+        int rc_ = (call);                         \
+        if (rc_ != GCRA_OK) return rc_;           \
+    } while (0)
+
+namespace {
+const __int128 NS_PER_S = 1000000000;
+
+struct RingSlot {
+    void *h_req = nullptr;
+    gcra_result *h_res = nullptr;
+    void *d_req = nullptr;
+    gcra_result *d_res = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_comp = nullptr, ev_done = nullptr;
+    bool in_flight = false;
+};
+}  // namespace
+
+struct gcra_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr, in_stream = nullptr, out_stream = nullptr;
+    Table tab{};
+    uint32_t total_lines = 0;
+    uint64_t capacity = 0;
+    // scratch for one batch
+    uint32_t max_batch = 0;
+    Req *drec = nullptr;
+    u64 *keys_a = nullptr, *keys_b = nullptr;
+    u32 *hist = nullptr, *tot = nullptr;
+    void *d_req = nullptr;
+    gcra_result *d_res = nullptr;
+    u32 *route_counts = nullptr;
+    PolicyDerived *d_pol = nullptr;
+    uint32_t npol = 0;
+    StoreOpResult *d_op = nullptr, *h_op = nullptr;
+    u64 *h_counters = nullptr;       // pinned snapshot, refreshed after every batch
+    cudaEvent_t ev_counters = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid = false;
+    uint64_t launches = 0;
+    uint64_t occupied_ub = 0;        // host-side upper bound of claimed slots
+    // store policy (mirrors the reference stores' fields)
+    int kind = GCRA_STORE_ADAPTIVE;
+    __int128 next_cleanup = 0, cleanup_interval = 0;
+    __int128 min_interval = 0, max_interval = 0, cur_interval = 0;
+    uint64_t expired_count = 0, ops_since_cleanup = 0, max_ops = 0;
+    uint64_t last_removed = 0, last_total = 0;
+    uint64_t ops_count = 0, cleanup_modulo = 0;
+    uint64_t seen_allowed = 0, seen_expired_hits = 0;
+    uint64_t n_sweeps = 0, n_grows = 0;
+    // ring
+    std::vector<RingSlot> ring;
+    uint32_t ring_cap = 0;
+    bool ring_compact = false;
+    std::string err;
+};
+
+static uint32_t ceil_log2(uint64_t x) {
+    uint32_t b = 0;
+    while ((1ULL << b) < x) b++;
+    return b;
+}
+
+static void table_geometry(uint64_t capacity, uint32_t &total_lines, uint32_t &nb_main, uint32_t &stash_slots) {
+    // first-fit two-choice buckets of 4 stay below ~0.4 % stash traffic up to load 0.5
+    uint64_t slots = 1ULL << ceil_log2(std::max<uint64_t>(capacity * 2, 256));
+    total_lines = (uint32_t)(slots / 4);
+    uint32_t ns = std::max<uint32_t>(total_lines / 64, 8);
+    nb_main = total_lines - ns;
+    stash_slots = (ns - 1) * 4;   // the last line is reserved (null slot)
+}
+
+static int alloc_table(gcra_engine *h, uint64_t capacity, Table &t, uint32_t &total_lines, u64 *counters) {
+    uint32_t nb, ss;
+    table_geometry(capacity, total_lines, nb, ss);
+    Line *lines = nullptr;
+    CK(cudaMalloc(&lines, (size_t)total_lines * sizeof(Line)));
+    t.lines = lines;
+    t.nb_main = nb;
+    t.stash_slots = ss;
+    t.null_slot = total_lines * 4 - 1;
+    t.slot_bits = ceil_log2((uint64_t)total_lines * 4);
+    t.counters = counters;
+    uint32_t grid = std::min<uint32_t>((total_lines + TILE_THREADS - 1) / TILE_THREADS, 148 * 16);
+    clear_lines_kernel<<<grid, TILE_THREADS, 0, h->stream>>>(lines, 0, total_lines);
+    h->launches++;
+    CK(cudaGetLastError());
+    return GCRA_OK;
+}
+
+static uint64_t load_limit(const gcra_engine *h) { return (uint64_t)h->tab.nb_main * 4 / 2; }
+
+static int refresh_counters(gcra_engine *h, bool wait) {
+    CK(cudaMemcpyAsync(h->h_counters, h->tab.counters, C_COUNT * sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaEventRecord(h->ev_counters, h->stream));
+    if (wait) CK(cudaEventSynchronize(h->ev_counters));
+    return GCRA_OK;
+}
+
+static int do_sweep(gcra_engine *h, int64_t now_ns, uint64_t *removed) {
+    CK(cudaSetDevice(h->device));
+    RC(refresh_counters(h, true));
+    uint64_t before = h->h_counters[C_SWEPT];
+    uint32_t grid = std::min<uint32_t>((h->total_lines + TILE_THREADS - 1) / TILE_THREADS, 148 * 8);
+    sweep_kernel<<<grid, TILE_THREADS, 0, h->stream>>>(h->tab, h->total_lines, now_ns);
+    h->launches++;
+    CK(cudaGetLastError());
+    RC(refresh_counters(h, true));
+    if (h->h_counters[C_STASH] == 0) {
+        // no key lives in the stash any more: drop its tombstones
+        uint32_t ns = h->total_lines - h->tab.nb_main;
+        clear_lines_kernel<<<(ns + TILE_THREADS - 1) / TILE_THREADS, TILE_THREADS, 0, h->stream>>>(
+            h->tab.lines, h->tab.nb_main, ns);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
+    h->occupied_ub = h->h_counters[C_OCCUPIED];
+    h->n_sweeps++;
+    if (removed) *removed = h->h_counters[C_SWEPT] - before;
+    return GCRA_OK;
+}
+
+// HashMap growth: rebuild into a table twice the size
+static int grow(gcra_engine *h, uint64_t need) {
+    CK(cudaStreamSynchronize(h->stream));
+    uint64_t newcap = std::max<uint64_t>(h->capacity * 2, 256);
+    while (newcap < need) newcap *= 2;
+    Table nt{};
+    uint32_t nl = 0;
+    u64 *ncounters = nullptr;
+    CK(cudaMalloc(&ncounters, C_COUNT * sizeof(u64)));
+    CK(cudaMemsetAsync(ncounters, 0, C_COUNT * sizeof(u64), h->stream));
+    int rc = alloc_table(h, newcap, nt, nl, ncounters);
+    if (rc) return rc;
+    uint32_t grid = std::min<uint32_t>((h->total_lines + TILE_THREADS - 1) / TILE_THREADS, 148 * 8);
+    rehash_kernel<<<grid, TILE_THREADS, 0, h->stream>>>(h->tab, h->total_lines, nt);
+    h->launches++;
+    CK(cudaGetLastError());
+    // carry the running totals over
+    RC(refresh_counters(h, true));
+    u64 keep[C_COUNT];
+    memcpy(keep, h->h_counters, sizeof(keep));
+    u64 fresh[C_COUNT];
+    CK(cudaMemcpyAsync(fresh, ncounters, sizeof(fresh), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (fresh[C_INSERT_FAIL]) { h->err = "table growth lost entries"; return GCRA_INTERNAL; }
+    keep[C_OCCUPIED] = fresh[C_OCCUPIED];
+    keep[C_REAL] = fresh[C_REAL];
+    keep[C_STASH] = fresh[C_STASH];
+    CK(cudaMemcpyAsync(ncounters, keep, sizeof(keep), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(h->tab.lines);
+    cudaFree(h->tab.counters);
+    h->tab = nt;
+    h->total_lines = nl;
+    h->capacity = newcap;
+    h->occupied_ub = keep[C_OCCUPIED];
+    h->n_grows++;
+    return GCRA_OK;
+}
+
+static int ensure_room(gcra_engine *h, uint64_t n) {
+    if (h->occupied_ub + n <= load_limit(h)) { h->occupied_ub += n; return GCRA_OK; }
+    int rc = refresh_counters(h, true);
+    if (rc) return rc;
+    h->occupied_ub = h->h_counters[C_OCCUPIED];
+    if (h->occupied_ub + n > load_limit(h)) {
+        rc = grow(h, (h->occupied_ub + n));
+        if (rc) return rc;
+    }
+    h->occupied_ub += n;
+    return GCRA_OK;
+}
+
+// ---- sweep policies ------------------------------------------------------------------------
+static bool adaptive_should_clean(const gcra_engine *h, __int128 now, uint64_t len) {   // adaptive_cleanup.rs:138-171
+    if (now >= h->next_cleanup) return true;
+    if (h->ops_since_cleanup >= h->max_ops) return true;
+    if (h->expired_count > 50) {
+        double ratio = (double)h->expired_count / (double)(len ? len : 1);
+        double threshold = (h->last_removed > h->last_total / 4) ? 0.2 / 2.0 : 0.2 * 1.25;
+        if (ratio > threshold) return true;
+    }
+    if (len > load_limit(h) * 3 / 4) return true;
+    return false;
+}
+
+// called at batch boundaries with the counters of the batches finished so far
+static int apply_policy(gcra_engine *h, int64_t now_ns) {
+    if (h->kind == GCRA_STORE_MANUAL) return GCRA_OK;
+    uint64_t allowed = h->h_counters[C_ALLOWED], hits = h->h_counters[C_EXPIRED_HITS];
+    uint64_t d_ops = allowed - h->seen_allowed, d_hits = hits - h->seen_expired_hits;
+    h->seen_allowed = allowed;
+    h->seen_expired_hits = hits;
+    __int128 now = now_ns;
+    uint64_t removed = 0;
+    if (h->kind == GCRA_STORE_PERIODIC) {                       // periodic.rs:128-142
+        if (now >= h->next_cleanup) {
+            int rc = do_sweep(h, now_ns, &removed);
+            if (rc) return rc;
+            h->expired_count = removed;
+            h->next_cleanup = now + h->cleanup_interval;
+        }
+    } else if (h->kind == GCRA_STORE_PROBABILISTIC) {           // probabilistic.rs:110-125
+        // sweep when some op count k in (ops, ops + d_ops] has k * 2654435761 % modulo == 0
+        const uint64_t c = 2654435761ULL, m = h->cleanup_modulo;
+        uint64_t a = h->ops_count + 1, b = h->ops_count + d_ops;
+        bool hit = false;
+        if (d_ops) {
+            if (b < (~0ULL) / c) {
+                uint64_t g = m, x = c % m;
+                while (x) { uint64_t tmp = g % x; g = x; x = tmp; }
+                uint64_t step = m / g;
+                hit = (b / step) > ((a - 1) / step);
+            } else {
+                for (uint64_t k = a; k <= b && !hit; k++) hit = ((k * c) % m) == 0;
+            }
+        }
+        h->ops_count = b;
+        if (hit) { int rc = do_sweep(h, now_ns, &removed); if (rc) return rc; }
+    } else {                                                    // adaptive_cleanup.rs:205-211
+        h->ops_since_cleanup += d_ops;
+        h->expired_count += d_hits;
+        uint64_t len = h->h_counters[C_REAL];
+        if (adaptive_should_clean(h, now, len)) {               // cleanup(): :173-203
+            int rc = do_sweep(h, now_ns, &removed);
+            if (rc) return rc;
+            if (removed == 0 && h->expired_count == 0) {
+                __int128 d = h->cur_interval * 2;
+                h->cur_interval = d < h->max_interval ? d : h->max_interval;
+            } else if ((double)removed > (double)len * 0.5) {
+                __int128 d = h->cur_interval / 2;
+                h->cur_interval = d > h->min_interval ? d : h->min_interval;
+            }
+            h->last_removed = removed;
+            h->last_total = len;
+            h->next_cleanup = now + h->cur_interval;
+            h->expired_count = 0;
+            h->ops_since_cleanup = 0;
+        }
+    }
+    return GCRA_OK;
+}
+
+// ---- one batch on a stream -------------------------------------------------------------------
+static int launch_batch(gcra_engine *h, uint32_t n, const void *d_req, bool compact, int64_t now_batch,
+                        gcra_result *d_res, cudaStream_t st, bool timed) {
+    if (n == 0) return GCRA_OK;
+    if (n > h->max_batch) { h->err = "batch larger than max_batch"; return GCRA_INTERNAL; }
+    if (compact && h->npol == 0) { h->err = "no policy table registered"; return GCRA_INTERNAL; }
+    int rc = ensure_room(h, n);
+    if (rc) return rc;
+    const uint32_t tiles = (n + TILE_THREADS - 1) / TILE_THREADS;
+    if (timed) CK(cudaEventRecord(h->ev[0], st));
+    if (compact)
+        ingest_kernel<true><<<tiles, TILE_THREADS, 0, st>>>(h->tab, d_req, h->d_pol, h->npol, now_batch, n,
+                                                            h->drec, h->keys_a, d_res);
+    else
+        ingest_kernel<false><<<tiles, TILE_THREADS, 0, st>>>(h->tab, d_req, nullptr, 0, 0, n, h->drec,
+                                                             h->keys_a, d_res);
+    h->launches++;
+    if (timed) CK(cudaEventRecord(h->ev[1], st));
+    // stable LSD radix sort over the slot bits
+    const uint32_t bits = h->tab.slot_bits;
+    const uint32_t passes = (bits + SORT_MAX_BITS - 1) / SORT_MAX_BITS;
+    const uint32_t stiles = (n + SORT_TILE - 1) / SORT_TILE;
+    u64 *src = h->keys_a, *dst = h->keys_b;
+    uint32_t shift = 32;
+    for (uint32_t p = 0; p < passes; p++) {
+        uint32_t pb = bits / passes + (p < bits % passes ? 1 : 0);
+        sort_hist_kernel<<<stiles, TILE_THREADS, 0, st>>>(src, n, shift, pb, stiles, h->hist);
+        sort_rowscan_kernel<<<1u << pb, TILE_THREADS, 0, st>>>(h->hist, stiles, h->tot);
+        sort_scatter_kernel<<<stiles, TILE_THREADS, 0, st>>>(src, dst, n, shift, pb, stiles, h->hist, h->tot);
+        h->launches += 3;
+        std::swap(src, dst);
+        shift += pb;
+    }
+    if (timed) CK(cudaEventRecord(h->ev[2], st));
+    const uint32_t warps = (n + 31) / 32;
+    decide_kernel<<<(warps + TILE_THREADS / 32 - 1) / (TILE_THREADS / 32), TILE_THREADS, 0, st>>>(
+        h->tab, src, h->drec, n, d_res);
+    h->launches++;
+    if (timed) { CK(cudaEventRecord(h->ev[3], st)); h->ev_valid = true; }
+    CK(cudaGetLastError());
+    return GCRA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int32_t gcra_create(const gcra_config *cfg, gcra_engine **out) {
+    if (!cfg || !out) return GCRA_INTERNAL;
+    *out = nullptr;
+    gcra_engine *h = new gcra_engine();
+    auto fail = [&](const char *what, cudaError_t e) {
+        fprintf(stderr, "gcra_create: %s: %s\n", what, cudaGetErrorString(e));
+        delete h;
+        return (int32_t)GCRA_INTERNAL;
+    };
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail("no CUDA device (this engine has no CPU path)", e);
+    if (cfg->device < 0 || cfg->device >= ndev) return fail("bad device ordinal", cudaErrorInvalidDevice);
+    h->device = cfg->device;
+    if ((e = cudaSetDevice(h->device)) != cudaSuccess) return fail("cudaSetDevice", e);
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
+    cudaStreamCreateWithFlags(&h->in_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking);
+    h->capacity = cfg->capacity ? cfg->capacity : 1000;      // DEFAULT_CAPACITY adaptive_cleanup.rs:10
+    h->max_batch = cfg->max_batch ? cfg->max_batch : (1u << 20);
+    u64 *counters = nullptr;
+    if ((e = cudaMalloc(&counters, C_COUNT * sizeof(u64))) != cudaSuccess) return fail("counters", e);
+    cudaMemsetAsync(counters, 0, C_COUNT * sizeof(u64), h->stream);
+    if (alloc_table(h, h->capacity, h->tab, h->total_lines, counters)) {
+        fprintf(stderr, "gcra_create: %s\n", h->err.c_str());
+        delete h;
+        return GCRA_INTERNAL;
+    }
+    const size_t mb = h->max_batch;
+    const uint32_t stiles = (uint32_t)((mb + SORT_TILE - 1) / SORT_TILE);
+    bool ok = cudaMalloc(&h->drec, mb * sizeof(Req)) == cudaSuccess &&
+              cudaMalloc(&h->keys_a, mb * sizeof(u64)) == cudaSuccess &&
+              cudaMalloc(&h->keys_b, mb * sizeof(u64)) == cudaSuccess &&
+              cudaMalloc(&h->hist, (size_t)SORT_MAX_DIGITS * stiles * sizeof(u32)) == cudaSuccess &&
+              cudaMalloc(&h->tot, SORT_MAX_DIGITS * sizeof(u32)) == cudaSuccess &&
+              cudaMalloc(&h->d_req, mb * sizeof(gcra_request)) == cudaSuccess &&
+              cudaMalloc(&h->d_res, mb * sizeof(gcra_result)) == cudaSuccess &&
+              cudaMalloc(&h->route_counts, (size_t)ROUTE_MAX_SHARDS * ((mb + TILE_THREADS - 1) / TILE_THREADS) * sizeof(u32)) == cudaSuccess &&
+              cudaMalloc(&h->d_op, 2 * sizeof(StoreOpResult)) == cudaSuccess &&
+              cudaMallocHost(&h->h_op, 2 * sizeof(StoreOpResult)) == cudaSuccess &&
+              cudaMallocHost(&h->h_counters, C_COUNT * sizeof(u64)) == cudaSuccess;
+    if (!ok) return fail("scratch allocation", cudaGetLastError());
+    memset(h->h_counters, 0, C_COUNT * sizeof(u64));
+    cudaEventCreateWithFlags(&h->ev_counters, cudaEventDisableTiming);
+    for (int i = 0; i < 4; i++) cudaEventCreate(&h->ev[i]);
+    // store policy, defaults as in the reference constructors
+    h->kind = cfg->store_kind;
+    __int128 created = cfg->created_ns;
+    if (h->kind == GCRA_STORE_PERIODIC) {
+        h->cleanup_interval = (__int128)(cfg->p0 ? cfg->p0 : 60) * NS_PER_S;       // periodic.rs:12
+        h->next_cleanup = created + h->cleanup_interval;
+    } else if (h->kind == GCRA_STORE_PROBABILISTIC) {
+        h->cleanup_modulo = cfg->p0 ? cfg->p0 : 1000;                               // probabilistic.rs:12
+    } else if (h->kind == GCRA_STORE_ADAPTIVE) {
+        h->min_interval = (__int128)(cfg->p0 ? cfg->p0 : 1) * NS_PER_S;            // adaptive_cleanup.rs:12-15
+        h->max_interval = (__int128)(cfg->p1 ? cfg->p1 : 300) * NS_PER_S;
+        h->max_ops = cfg->p2 ? cfg->p2 : 100000;
+        h->cur_interval = 5 * NS_PER_S;
+        h->next_cleanup = created + 5 * NS_PER_S;
+    }
+    if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return fail("init", e);
+    *out = h;
+    return GCRA_OK;
+}
+
+void gcra_destroy(gcra_engine *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (auto &s : h->ring) {
+        cudaFreeHost(s.h_req); cudaFreeHost(s.h_res); cudaFree(s.d_req); cudaFree(s.d_res);
+        cudaEventDestroy(s.ev_in); cudaEventDestroy(s.ev_comp); cudaEventDestroy(s.ev_done);
+    }
+    cudaFree(h->tab.lines); cudaFree(h->tab.counters);
+    cudaFree(h->drec); cudaFree(h->keys_a); cudaFree(h->keys_b); cudaFree(h->hist); cudaFree(h->tot);
+    cudaFree(h->d_req); cudaFree(h->d_res); cudaFree(h->route_counts); cudaFree(h->d_pol); cudaFree(h->d_op);
+    cudaFreeHost(h->h_op); cudaFreeHost(h->h_counters);
+    cudaEventDestroy(h->ev_counters);
+    for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]);
+    cudaStreamDestroy(h->stream); cudaStreamDestroy(h->in_stream); cudaStreamDestroy(h->out_stream);
+    delete h;
+}
+
+const char *gcra_last_error(gcra_engine *h) { return h ? h->err.c_str() : "null handle"; }
+
+uint64_t gcra_hash_key(const void *key, uint64_t len) {
+    const unsigned char *p = (const unsigned char *)key;
+    uint64_t hsh = 0x2545F4914F6CDD1DULL ^ (len * 0x9E3779B97F4A7C15ULL);
+    while (len >= 8) {
+        uint64_t w;
+        memcpy(&w, p, 8);
+        hsh = mix64(hsh ^ w) + 0xD1B54A32D192ED03ULL;
+        p += 8; len -= 8;
+    }
+    if (len) {
+        uint64_t w = 0;
+        memcpy(&w, p, len);
+        hsh = mix64(hsh ^ w ^ (len << 56));
+    }
+    return mix64(hsh);
+}
+
+void gcra_hash_key_ids(const void *prefix, uint64_t prefix_len, const uint64_t *ids, uint64_t n, uint64_t *out) {
+    char buf[96];
+    if (prefix_len > 64) prefix_len = 64;
+    memcpy(buf, prefix, prefix_len);
+    for (uint64_t i = 0; i < n; i++) {
+        char tmp[24];
+        int k = 0;
+        uint64_t v = ids[i];
+        do { tmp[k++] = (char)('0' + v % 10); v /= 10; } while (v);
+        for (int j = 0; j < k; j++) buf[prefix_len + j] = tmp[k - 1 - j];
+        out[i] = gcra_hash_key(buf, prefix_len + k);
+    }
+}
+
+int32_t gcra_derive_params(int64_t max_burst, int64_t count, int64_t period, int64_t *ei, int64_t *dvt) {
+    i64 a = 0, b = 0;
+    int st = derive_params(max_burst, count, period, &a, &b);
+    if (ei) *ei = a;
+    if (dvt) *dvt = b;
+    return st;
+}
+
+static int store_op(gcra_engine *h, int op, uint64_t key_hash, int64_t a, int64_t b, uint64_t ttl, int64_t now) {
+    CK(cudaSetDevice(h->device));
+    if (op == 2) { int rc = ensure_room(h, 1); if (rc) return rc; }
+    store_op_kernel<<<1, 1, 0, h->stream>>>(h->tab, op, stored_key(key_hash), a, b, ttl, now, h->d_op);
+    h->launches++;
+    CK(cudaMemcpyAsync(h->h_op, h->d_op, 2 * sizeof(StoreOpResult), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return GCRA_OK;
+}
+
+static int policy_before_mutation(gcra_engine *h, int64_t now_ns) {
+    // the reference's mutating ops start with maybe_clean_expired(now) (adaptive_cleanup.rs:229,261)
+    int rc = refresh_counters(h, true);
+    if (rc) return rc;
+    return apply_policy(h, now_ns);
+}
+
+int32_t gcra_store_get(gcra_engine *h, const void *key, uint64_t len, int64_t now_ns, int64_t *value,
+                       uint8_t *found) {
+    int rc = store_op(h, 0, gcra_hash_key(key, len), 0, 0, 0, now_ns);
+    if (rc) return rc;
+    if (found) *found = (uint8_t)h->h_op[0].flag;
+    if (value) *value = h->h_op[0].value;
+    return GCRA_OK;
+}
+
+int32_t gcra_store_cas(gcra_engine *h, const void *key, uint64_t len, int64_t old_value, int64_t new_value,
+                       uint64_t ttl_ns, int64_t now_ns, uint8_t *swapped) {
+    int rc = policy_before_mutation(h, now_ns);
+    if (rc) return rc;
+    rc = store_op(h, 1, gcra_hash_key(key, len), old_value, new_value, ttl_ns, now_ns);
+    if (rc) return rc;
+    if (swapped) *swapped = (uint8_t)h->h_op[0].flag;
+    return GCRA_OK;
+}
+
+int32_t gcra_store_set_nx(gcra_engine *h, const void *key, uint64_t len, int64_t value, uint64_t ttl_ns,
+                          int64_t now_ns, uint8_t *stored) {
+    int rc = policy_before_mutation(h, now_ns);
+    if (rc) return rc;
+    rc = store_op(h, 2, gcra_hash_key(key, len), value, 0, ttl_ns, now_ns);
+    if (rc) return rc;
+    if (h->h_op[0].status) { h->err = "table full"; return GCRA_INTERNAL; }
+    if (stored) *stored = (uint8_t)h->h_op[0].flag;
+    return GCRA_OK;
+}
+
+int32_t gcra_rate_limit_batch_device(gcra_engine *h, uint64_t n, const gcra_request *d_req, gcra_result *d_res,
+                                     void *stream) {
+    CK(cudaSetDevice(h->device));
+    return launch_batch(h, (uint32_t)n, d_req, false, 0, d_res, stream ? (cudaStream_t)stream : h->stream, true);
+}
+
+int32_t gcra_rate_limit_batch16_device(gcra_engine *h, uint64_t n, const gcra_request16 *d_req, int64_t now_ns,
+                                       gcra_result *d_res, void *stream) {
+    CK(cudaSetDevice(h->device));
+    return launch_batch(h, (uint32_t)n, d_req, true, now_ns, d_res, stream ? (cudaStream_t)stream : h->stream, true);
+}
+
+static int host_batch(gcra_engine *h, uint64_t n, const void *req, size_t rsz, bool compact, int64_t now_batch,
+                      gcra_result *res) {
+    CK(cudaSetDevice(h->device));
+    uint64_t done = 0;
+    while (done < n) {
+        uint32_t m = (uint32_t)std::min<uint64_t>(n - done, h->max_batch);
+        const unsigned char *src = (const unsigned char *)req + done * rsz;
+        CK(cudaMemcpyAsync(h->d_req, src, (size_t)m * rsz, cudaMemcpyHostToDevice, h->stream));
+        int rc = launch_batch(h, m, h->d_req, compact, now_batch, h->d_res, h->stream, true);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(res + done, h->d_res, (size_t)m * sizeof(gcra_result), cudaMemcpyDeviceToHost, h->stream));
+        RC(refresh_counters(h, false));
+        CK(cudaStreamSynchronize(h->stream));
+        int64_t now_hint = compact ? now_batch : ((const gcra_request *)req)[done + m - 1].now_ns;
+        rc = apply_policy(h, now_hint);
+        if (rc) return rc;
+        done += m;
+    }
+    return GCRA_OK;
+}
+
+int32_t gcra_rate_limit_batch(gcra_engine *h, uint64_t n, const gcra_request *req, gcra_result *res) {
+    return host_batch(h, n, req, sizeof(gcra_request), false, 0, res);
+}
+
+int32_t gcra_rate_limit_batch16(gcra_engine *h, uint64_t n, const gcra_request16 *req, int64_t now_ns,
+                                gcra_result *res) {
+    return host_batch(h, n, req, sizeof(gcra_request16), true, now_ns, res);
+}
+
+int32_t gcra_rate_limit(gcra_engine *h, const void *key, uint64_t len, int64_t max_burst, int64_t count_per_period,
+                        int64_t period, int64_t quantity, int64_t now_ns, gcra_result *out) {
+    gcra_request r = {gcra_hash_key(key, len), max_burst, count_per_period, period, quantity, now_ns};
+    gcra_result tmp;
+    int rc = host_batch(h, 1, &r, sizeof(r), false, 0, &tmp);
+    if (rc) { if (out) { memset(out, 0, sizeof(*out)); out->status = GCRA_INTERNAL; } return rc; }
+    if (out) *out = tmp;
+    if (tmp.status == GCRA_INTERNAL) h->err = "rate_limit: internal (duration overflow, pre-epoch time or table full)";
+    return tmp.status;
+}
+
+int32_t gcra_set_policies(gcra_engine *h, uint32_t n, const gcra_policy *policies) {
+    CK(cudaSetDevice(h->device));
+    std::vector<PolicyDerived> pd(n);
+    for (uint32_t i = 0; i < n; i++) {
+        const gcra_policy &p = policies[i];
+        pd[i].ei = pd[i].dvt = 0; pd[i].pad = 0;
+        if (p.max_burst <= 0 || p.count_per_period <= 0 || p.period <= 0) pd[i].status = GCRA_INVALID_RATE_LIMIT;
+        else pd[i].status = derive_params(p.max_burst, p.count_per_period, p.period, &pd[i].ei, &pd[i].dvt);
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_pol);
+    h->d_pol = nullptr;
+    h->npol = 0;
+    if (n) {
+        CK(cudaMalloc(&h->d_pol, n * sizeof(PolicyDerived)));
+        CK(cudaMemcpy(h->d_pol, pd.data(), n * sizeof(PolicyDerived), cudaMemcpyHostToDevice));
+        h->npol = n;
+    }
+    return GCRA_OK;
+}
+
+// ---- ring --------------------------------------------------------------------------------------
+int32_t gcra_ring_create(gcra_engine *h, uint32_t slots, uint32_t slot_capacity, int32_t compact) {
+    CK(cudaSetDevice(h->device));
+    if (!h->ring.empty()) { h->err = "ring already created"; return GCRA_INTERNAL; }
+    if (slot_capacity == 0 || slot_capacity > h->max_batch) { h->err = "slot_capacity must be in 1..max_batch"; return GCRA_INTERNAL; }
+    h->ring_cap = slot_capacity;
+    h->ring_compact = compact != 0;
+    size_t rsz = compact ? sizeof(gcra_request16) : sizeof(gcra_request);
+    h->ring.resize(slots);
+    for (auto &s : h->ring) {
+        CK(cudaMallocHost(&s.h_req, slot_capacity * rsz));
+        CK(cudaMallocHost(&s.h_res, slot_capacity * sizeof(gcra_result)));
+        CK(cudaMalloc(&s.d_req, slot_capacity * rsz));
+        CK(cudaMalloc(&s.d_res, slot_capacity * sizeof(gcra_result)));
+        CK(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s.ev_comp, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+    }
+    return GCRA_OK;
+}
+
+void *gcra_ring_requests(gcra_engine *h, uint32_t slot) { return slot < h->ring.size() ? h->ring[slot].h_req : nullptr; }
+gcra_result *gcra_ring_results(gcra_engine *h, uint32_t slot) { return slot < h->ring.size() ? h->ring[slot].h_res : nullptr; }
+
+int32_t gcra_ring_submit(gcra_engine *h, uint32_t slot, uint32_t n, int64_t now_ns) {
+    CK(cudaSetDevice(h->device));
+    if (slot >= h->ring.size() || n > h->ring_cap) { h->err = "bad ring slot / size"; return GCRA_INTERNAL; }
+    RingSlot &s = h->ring[slot];
+    if (s.in_flight) { h->err = "ring slot still in flight"; return GCRA_INTERNAL; }
+    // sweep policy with the counters of the batches finished so far (no stall)
+    if (cudaEventQuery(h->ev_counters) == cudaSuccess) { int rc = apply_policy(h, now_ns); if (rc) return rc; }
+    size_t rsz = h->ring_compact ? sizeof(gcra_request16) : sizeof(gcra_request);
+    CK(cudaMemcpyAsync(s.d_req, s.h_req, (size_t)n * rsz, cudaMemcpyHostToDevice, h->in_stream));
+    CK(cudaEventRecord(s.ev_in, h->in_stream));
+    CK(cudaStreamWaitEvent(h->stream, s.ev_in, 0));
+    int rc = launch_batch(h, n, s.d_req, h->ring_compact, now_ns, s.d_res, h->stream, false);
+    if (rc) return rc;
+    CK(cudaEventRecord(s.ev_comp, h->stream));
+    RC(refresh_counters(h, false));
+    CK(cudaStreamWaitEvent(h->out_stream, s.ev_comp, 0));
+    CK(cudaMemcpyAsync(s.h_res, s.d_res, (size_t)n * sizeof(gcra_result), cudaMemcpyDeviceToHost, h->out_stream));
+    CK(cudaEventRecord(s.ev_done, h->out_stream));
+    s.in_flight = true;
+    return GCRA_OK;
+}
+
+int32_t gcra_ring_wait(gcra_engine *h, uint32_t slot) {
+    if (slot >= h->ring.size()) { h->err = "bad ring slot"; return GCRA_INTERNAL; }
+    RingSlot &s = h->ring[slot];
+    if (!s.in_flight) return GCRA_OK;
+    CK(cudaEventSynchronize(s.ev_done));
+    s.in_flight = false;
+    return GCRA_OK;
+}
+
+int32_t gcra_ring_poll(gcra_engine *h, uint32_t slot, int32_t *done) {
+    if (slot >= h->ring.size()) { h->err = "bad ring slot"; return GCRA_INTERNAL; }
+    RingSlot &s = h->ring[slot];
+    if (!s.in_flight) { *done = 1; return GCRA_OK; }
+    cudaError_t e = cudaEventQuery(s.ev_done);
+    if (e == cudaSuccess) { s.in_flight = false; *done = 1; return GCRA_OK; }
+    if (e == cudaErrorNotReady) { *done = 0; return GCRA_OK; }
+    h->err = cudaGetErrorString(e);
+    return GCRA_INTERNAL;
+}
+
+// ---- sweep / introspection ---------------------------------------------------------------------
+int32_t gcra_sweep(gcra_engine *h, int64_t now_ns, uint64_t *removed) { return do_sweep(h, now_ns, removed); }
+
+uint64_t gcra_len(gcra_engine *h) {
+    cudaSetDevice(h->device);
+    if (refresh_counters(h, true)) return 0;
+    return h->h_counters[C_REAL];
+}
+
+int32_t gcra_get_stats(gcra_engine *h, gcra_stats *out) {
+    CK(cudaSetDevice(h->device));
+    int rc = refresh_counters(h, true);
+    if (rc) return rc;
+    const u64 *c = h->h_counters;
+    out->len = c[C_REAL];
+    out->occupied_slots = c[C_OCCUPIED];
+    out->table_slots = (uint64_t)h->total_lines * 4;
+    out->stash_entries = c[C_STASH];
+    out->allowed = c[C_ALLOWED];
+    out->denied = c[C_DENIED];
+    out->errors = c[C_ERRORS];
+    out->expired_hits = c[C_EXPIRED_HITS];
+    out->sweeps = h->n_sweeps;
+    out->swept = c[C_SWEPT];
+    out->grows = h->n_grows;
+    return GCRA_OK;
+}
+
+int32_t gcra_peek(gcra_engine *h, uint64_t key_hash, int64_t *tat, int64_t *expiry_ns, uint8_t *found) {
+    int rc = store_op(h, 3, key_hash, 0, 0, 0, 0);
+    if (rc) return rc;
+    *found = (uint8_t)h->h_op[0].flag;
+    if (*found) { *tat = h->h_op[0].value; *expiry_ns = h->h_op[1].value; }
+    return GCRA_OK;
+}
+
+int32_t gcra_sync(gcra_engine *h) {
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->in_stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaStreamSynchronize(h->out_stream));
+    return GCRA_OK;
+}
+
+int32_t gcra_last_kernel_ms(gcra_engine *h, float out[4]) {
+    if (!h->ev_valid) { h->err = "no timed batch yet"; return GCRA_INTERNAL; }
+    CK(cudaEventSynchronize(h->ev[3]));
+    CK(cudaEventElapsedTime(&out[0], h->ev[0], h->ev[3]));
+    CK(cudaEventElapsedTime(&out[1], h->ev[0], h->ev[1]));
+    CK(cudaEventElapsedTime(&out[2], h->ev[1], h->ev[2]));
+    CK(cudaEventElapsedTime(&out[3], h->ev[2], h->ev[3]));
+    return GCRA_OK;
+}
+
+uint64_t gcra_launch_count(gcra_engine *h) { return h->launches; }
+
+// ---- routing -------------------------------------------------------------------------------------
+uint32_t gcra_owner_of(uint64_t key_hash, uint32_t n_shards) { return owner_of(key_hash, n_shards); }
+
+int32_t gcra_route_partition(gcra_engine *h, uint64_t n, const gcra_request *d_req, uint32_t n_shards,
+                             gcra_request *d_out, uint32_t *d_src_index, uint32_t *d_counts, void *stream) {
+    CK(cudaSetDevice(h->device));
+    if (n_shards == 0 || n_shards > ROUTE_MAX_SHARDS || n > h->max_batch) { h->err = "bad shard count / batch size"; return GCRA_INTERNAL; }
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    if (n == 0) { CK(cudaMemsetAsync(d_counts, 0, n_shards * sizeof(u32), st)); return GCRA_OK; }
+    uint32_t tiles = (uint32_t)((n + TILE_THREADS - 1) / TILE_THREADS);
+    route_count_kernel<<<tiles, TILE_THREADS, 0, st>>>(d_req, (u32)n, n_shards, tiles, h->route_counts);
+    route_scan_kernel<<<1, TILE_THREADS, 0, st>>>(h->route_counts, n_shards, tiles, d_counts);
+    route_scatter_kernel<<<tiles, TILE_THREADS, 0, st>>>(d_req, (u32)n, n_shards, tiles, h->route_counts, d_out, d_src_index);
+    h->launches += 3;
+    CK(cudaGetLastError());
+    return GCRA_OK;
+}
+
+int32_t gcra_route_unpermute(gcra_engine *h, uint64_t n, const gcra_result *d_res_routed, const uint32_t *d_src_index,
+                             gcra_result *d_res, void *stream) {
+    CK(cudaSetDevice(h->device));
+    if (n == 0) return GCRA_OK;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    route_unpermute_kernel<<<(uint32_t)((n + TILE_THREADS - 1) / TILE_THREADS), TILE_THREADS, 0, st>>>(
+        d_res_routed, d_src_index, (u32)n, d_res);
+    h->launches++;
+    CK(cudaGetLastError());
+    return GCRA_OK;
+}
+
+}  // extern "C"

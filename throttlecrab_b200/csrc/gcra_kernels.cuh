@@ -1,0 +1,713 @@
+// gcra_kernels.cuh -- the sm_100a kernels of the batched GCRA engine.
+//
+//   K1a ingest  : bulk-async (TMA, UBLKCP) staging of a request tile into shared memory, per-request
+//                 validation + parameter derivation (rate_limiter.rs:111-122), key -> slot probe/claim
+//   K1b order   : stable LSD radix sort of (slot, index) so that requests on one key are adjacent and
+//                 in index order -- the reference applies requests strictly one at a time
+//                 (throttlecrab-server/src/actor.rs:217-236)
+//   K1c decide  : warp-cooperative GCRA compare-and-update (rate_limiter.rs:150-248); duplicates of a
+//                 key inside a batch are resolved exactly by speculate-and-commit over warp ballots
+//   K2  sweep   : HashMap::retain(expiry > now) (adaptive_cleanup.rs:176-182) as a streaming scan
+//   K3  route   : stable partition of a batch by owner shard for the multi-GPU all-to-all
+#pragma once
+#include "gcra_device.cuh"
+#include "../../include/gcra_b200.h"
+
+namespace gcra {
+
+constexpr int TILE_THREADS = 256;
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier + 1-D bulk async copy (TMA) helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 smem_u32(const void *p) {
+    return (u32)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u32 bytes, u64 *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1a: ingest
+// ---------------------------------------------------------------------------------------------
+struct PolicyDerived { i64 ei, dvt; int status; int pad; };
+
+__device__ __forceinline__ void write_result(gcra_result *out, i64 remaining, i64 reset, i64 retry,
+                                             int status, int allowed) {
+    longlong2 a = make_longlong2(remaining, reset);
+    longlong2 b;
+    b.x = retry;
+    b.y = (i64)(u32)status | ((i64)(allowed & 0xff) << 32);
+    reinterpret_cast<longlong2 *>(out)[0] = a;
+    reinterpret_cast<longlong2 *>(out)[1] = b;
+}
+
+template <bool COMPACT>
+__global__ void __launch_bounds__(TILE_THREADS)
+ingest_kernel(Table t, const void *__restrict__ req_base, const PolicyDerived *__restrict__ pol,
+              u32 npol, i64 now_batch, u32 n, Req *__restrict__ drec, u64 *__restrict__ sortkeys,
+              gcra_result *__restrict__ out) {
+    constexpr u32 RSZ = COMPACT ? sizeof(gcra_request16) : sizeof(gcra_request);
+    __shared__ __align__(128) unsigned char stage[TILE_THREADS * RSZ];
+    __shared__ __align__(8) u64 bar;
+
+    const u32 base = blockIdx.x * TILE_THREADS;
+    const u32 cnt = min((u32)TILE_THREADS, n - base);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, cnt * RSZ);
+        bulk_g2s(stage, (const unsigned char *)req_base + (size_t)base * RSZ, cnt * RSZ, &bar);
+    }
+    mbar_wait(&bar, 0);
+
+    const u32 i = base + threadIdx.x;
+    const bool in_range = threadIdx.x < cnt;
+    int status = 0;
+    u64 key_hash = 0;
+    Req r = {0, 0, 0, 0};
+    if (in_range) {
+        if (COMPACT) {
+            const gcra_request16 *q = reinterpret_cast<const gcra_request16 *>(stage) + threadIdx.x;
+            ulonglong2 w = *reinterpret_cast<const ulonglong2 *>(q);
+            key_hash = w.x;
+            int qty = (int)(u32)(w.y & 0xffffffffULL);
+            u32 p = (u32)(w.y >> 32);
+            r.q = qty;
+            r.now = now_batch;
+            if (qty < 0) status = GCRA_NEGATIVE_QUANTITY;          // rate_limiter.rs:111-113
+            else if (p >= npol) status = GCRA_INTERNAL;
+            else {
+                PolicyDerived pd = pol[p];
+                status = pd.status;
+                r.ei = pd.ei;
+                r.dvt = pd.dvt;
+            }
+        } else {
+            const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(
+                reinterpret_cast<const gcra_request *>(stage) + threadIdx.x);
+            ulonglong2 w0 = q[0], w1 = q[1], w2 = q[2];
+            key_hash = w0.x;
+            i64 max_burst = (i64)w0.y, count = (i64)w1.x, period = (i64)w1.y;
+            r.q = (i64)w2.x;
+            r.now = (i64)w2.y;
+            if (r.q < 0) status = GCRA_NEGATIVE_QUANTITY;          // :111-113
+            else if (max_burst <= 0 || count <= 0 || period <= 0) status = GCRA_INVALID_RATE_LIMIT;  // :115-117
+            else status = derive_params(max_burst, count, period, &r.ei, &r.dvt);
+        }
+        // a pre-epoch `now` makes the reference read the wall clock (:128-143): not reproducible
+        if (status == 0 && r.now < 0) status = GCRA_INTERNAL;
+    }
+
+    u32 slot = t.null_slot;
+    bool fresh = false;
+    if (in_range && status == 0) {
+        slot = find_or_claim(t, stored_key(key_hash), fresh);
+        if (slot == t.null_slot) status = GCRA_INTERNAL;   // table full
+        else if (fresh) t.lines[slot >> 2].off[slot & 3] = (u64)EXP_PHANTOM;
+    }
+    if (in_range) {
+        reinterpret_cast<longlong2 *>(drec + i)[0] = make_longlong2(r.now, r.ei);
+        reinterpret_cast<longlong2 *>(drec + i)[1] = make_longlong2(r.dvt, r.q);
+        sortkeys[i] = ((u64)slot << 32) | i;
+        if (status != 0) write_result(out + i, 0, 0, 0, status, 0);
+    }
+    // warp-aggregated counters
+    u32 mf = __ballot_sync(0xffffffffu, fresh);
+    u32 me = __ballot_sync(0xffffffffu, in_range && status != 0);
+    if ((threadIdx.x & 31) == 0) {
+        if (mf) atomicAdd(&t.counters[C_OCCUPIED], (u64)__popc(mf));
+        if (me) atomicAdd(&t.counters[C_ERRORS], (u64)__popc(me));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1b: stable LSD radix sort on the slot bits of (slot << 32 | index)
+// ---------------------------------------------------------------------------------------------
+constexpr int SORT_ITEMS = 4;                              // items per thread
+constexpr int SORT_TILE = TILE_THREADS * SORT_ITEMS;       // 1024 keys per CTA
+constexpr int SORT_MAX_BITS = 9;
+constexpr int SORT_MAX_DIGITS = 1 << SORT_MAX_BITS;
+
+__global__ void __launch_bounds__(TILE_THREADS)
+sort_hist_kernel(const u64 *__restrict__ in, u32 n, u32 shift, u32 bits, u32 num_tiles,
+                 u32 *__restrict__ hist) {
+    __shared__ u32 h[SORT_MAX_DIGITS];
+    const u32 nd = 1u << bits, mask = nd - 1;
+    for (u32 d = threadIdx.x; d < nd; d += TILE_THREADS) h[d] = 0;
+    __syncthreads();
+    const u32 base = blockIdx.x * SORT_TILE;
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; k++) {
+        u32 i = base + k * TILE_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&h[(u32)(in[i] >> shift) & mask], 1u);
+    }
+    __syncthreads();
+    for (u32 d = threadIdx.x; d < nd; d += TILE_THREADS) hist[(size_t)d * num_tiles + blockIdx.x] = h[d];
+}
+
+// one CTA per digit: exclusive scan of that digit's per-tile counts, digit total to tot[d]
+__global__ void __launch_bounds__(TILE_THREADS)
+sort_rowscan_kernel(u32 *__restrict__ hist, u32 num_tiles, u32 *__restrict__ tot) {
+    __shared__ u32 part[TILE_THREADS];
+    u32 *row = hist + (size_t)blockIdx.x * num_tiles;
+    const u32 per = (num_tiles + TILE_THREADS - 1) / TILE_THREADS;
+    const u32 lo = min(threadIdx.x * per, num_tiles), hi = min(lo + per, num_tiles);
+    u32 s = 0;
+    for (u32 i = lo; i < hi; i++) s += row[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    // block exclusive scan (Hillis-Steele on 256 partials)
+    for (u32 off = 1; off < TILE_THREADS; off <<= 1) {
+        u32 v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    u32 acc = part[threadIdx.x] - s;
+    for (u32 i = lo; i < hi; i++) { u32 v = row[i]; row[i] = acc; acc += v; }
+    if (threadIdx.x == TILE_THREADS - 1) tot[blockIdx.x] = part[TILE_THREADS - 1];
+}
+
+__global__ void __launch_bounds__(TILE_THREADS)
+sort_scatter_kernel(const u64 *__restrict__ in, u64 *__restrict__ outk, u32 n, u32 shift, u32 bits,
+                    u32 num_tiles, const u32 *__restrict__ hist, const u32 *__restrict__ tot) {
+    constexpr int NW = TILE_THREADS / 32;
+    __shared__ u32 cnt[NW][SORT_MAX_DIGITS];   // per-warp digit counters -> per-warp offsets
+    __shared__ u32 gbase[SORT_MAX_DIGITS];     // global base of (digit, this tile)
+    const u32 nd = 1u << bits, mask = nd - 1;
+    const u32 w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (u32 d = threadIdx.x; d < nd; d += TILE_THREADS) {
+#pragma unroll
+        for (int x = 0; x < NW; x++) cnt[x][d] = 0;
+        gbase[d] = tot[d];
+    }
+    __syncthreads();
+    // exclusive scan of the digit totals (Hillis-Steele, nd <= 512, two elements per thread)
+    for (u32 off = 1; off < nd; off <<= 1) {
+        u32 v0 = 0, v1 = 0;
+        u32 d0 = threadIdx.x, d1 = threadIdx.x + TILE_THREADS;
+        if (d0 < nd && d0 >= off) v0 = gbase[d0 - off];
+        if (d1 < nd && d1 >= off) v1 = gbase[d1 - off];
+        __syncthreads();
+        if (d0 < nd) gbase[d0] += v0;
+        if (d1 < nd) gbase[d1] += v1;
+        __syncthreads();
+    }
+    for (u32 d = threadIdx.x; d < nd; d += TILE_THREADS)
+        gbase[d] = gbase[d] - tot[d] + hist[(size_t)d * num_tiles + blockIdx.x];
+    // warp w owns tile elements [w*128, w*128+128): item k, lane l -> w*128 + k*32 + l (index order)
+    const u32 base = blockIdx.x * SORT_TILE + w * (32 * SORT_ITEMS);
+    u64 key[SORT_ITEMS];
+    u32 dig[SORT_ITEMS], rank[SORT_ITEMS];
+    const u32 lt = (1u << lane) - 1;
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; k++) {
+        u32 i = base + k * 32 + lane;
+        bool valid = i < n;
+        key[k] = valid ? in[i] : 0;
+        dig[k] = (u32)(key[k] >> shift) & mask;
+        u32 peers = __match_any_sync(0xffffffffu, valid ? dig[k] : (0x80000000u | lane));
+        u32 before = valid ? cnt[w][dig[k]] : 0;
+        rank[k] = before + __popc(peers & lt);
+        __syncwarp();
+        if (valid && (peers & lt) == 0) cnt[w][dig[k]] = before + __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    // per digit: exclusive scan over the warps
+    for (u32 d = threadIdx.x; d < nd; d += TILE_THREADS) {
+        u32 acc = 0;
+#pragma unroll
+        for (int x = 0; x < NW; x++) { u32 v = cnt[x][d]; cnt[x][d] = acc; acc += v; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; k++) {
+        u32 i = base + k * 32 + lane;
+        if (i < n) outk[gbase[dig[k]] + cnt[w][dig[k]] + rank[k]] = key[k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1c: decide -- the GCRA theoretical-arrival-time compare-and-update
+// ---------------------------------------------------------------------------------------------
+// Sorted positions are cut into chunks of 32, one warp per chunk.  A run of equal slots (all
+// requests of one key, in index order) is owned by the warp whose chunk holds the run's first
+// element; when a run crosses the chunk end that warp keeps walking it chunk by chunk, carrying
+// the key's state in registers, and the warps of the following chunks skip those lanes.
+//
+// Inside a chunk every lane evaluates its request against the state its run currently has.
+// A request that is denied (or leaves the entry bit-for-bit unchanged) does not alter what later
+// requests see, so all lanes up to and including the first state-changing lane of a run are final;
+// that lane's new state is shuffled to the lanes behind it and only they re-evaluate.  The loop
+// runs (state changes in the busiest run of the chunk + 1) times, and yields exactly the results
+// of applying the requests one after another.
+struct RunState { i64 tat, exp, ei; };
+
+struct LaneOut { Decision d; bool done; };
+
+__device__ __forceinline__ void run_chunk(u32 lane, bool mine, u32 gmask, const Req &r, RunState &s,
+                                          Decision &fin, bool &changed_any, u32 &n_exp_hits) {
+    // on return: fin = this lane's decision; s = state after this lane (its run's state)
+    const u32 lt = (1u << lane) - 1;
+    bool pending = mine;
+    bool mflag = false;
+    for (;;) {
+        Decision d;
+        bool mut = false;
+        RunState so = s;
+        if (pending) {
+            d = decide(s.tat, s.exp, r);
+            if (d.allowed) {
+                so.tat = d.new_tat; so.exp = d.new_exp; so.ei = r.ei;
+                mut = (so.tat != s.tat) | (so.exp != s.exp) | (so.ei != s.ei);
+            }
+        }
+        const u32 P = __ballot_sync(0xffffffffu, pending);
+        if (P == 0) break;
+        const u32 M = __ballot_sync(0xffffffffu, pending && mut);
+        const u32 prior = M & gmask & lt;
+        const int src = prior ? (__ffs(prior) - 1) : (int)lane;
+        RunState sn;
+        sn.tat = __shfl_sync(0xffffffffu, so.tat, src);
+        sn.exp = __shfl_sync(0xffffffffu, so.exp, src);
+        sn.ei = __shfl_sync(0xffffffffu, so.ei, src);
+        if (pending) {
+            if (prior == 0) {
+                fin = d;
+                // a write over an entry that exists but is expired (adaptive_cleanup.rs:233,267)
+                if (d.allowed && !d.live && s.exp >= 0) n_exp_hits++;
+                if (mut) { s = so; mflag = true; }
+                pending = false;
+            } else {
+                s = sn;
+            }
+        }
+    }
+    changed_any = mflag;
+}
+
+__global__ void __launch_bounds__(TILE_THREADS)
+decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ drec, u32 n,
+              gcra_result *__restrict__ out) {
+    const u32 lane = threadIdx.x & 31;
+    const u32 warp_global = (blockIdx.x * TILE_THREADS + threadIdx.x) >> 5;
+    u32 base = warp_global * 32;
+    if (base >= n) return;   // whole warp
+
+    u32 pos = base + lane;
+    u64 e = pos < n ? sorted[pos] : ~0ULL;
+    u32 slot = (u32)(e >> 32);
+    bool valid = pos < n && slot != t.null_slot;
+    // slot of the element just before this chunk
+    u32 prev_last = base > 0 ? (u32)(sorted[base - 1] >> 32) : 0xffffffffu;
+    u32 prev = __shfl_up_sync(0xffffffffu, slot, 1);
+    if (lane == 0) prev = prev_last;
+    // lanes continuing a run that started in an earlier chunk belong to that chunk's warp
+    const u32 slot0 = __shfl_sync(0xffffffffu, slot, 0);
+    const u32 same0 = __ballot_sync(0xffffffffu, valid && slot == slot0);
+    // sorted => same0 is a prefix of lanes
+    const u32 foreign = (base > 0 && slot0 == prev_last) ? same0 : 0;
+    bool mine = valid && !((foreign >> lane) & 1);
+    bool head = mine && (slot != prev || (lane > 0 && ((foreign >> (lane - 1)) & 1)));
+    const u32 heads = __ballot_sync(0xffffffffu, head);
+    const u32 le = (lane == 31) ? 0xffffffffu : ((2u << lane) - 1);
+    const int hl = mine ? (31 - __clz(heads & le)) : (int)lane;
+    const u32 gmask = __match_any_sync(0xffffffffu, mine ? hl : (int)(32 + lane));
+
+    Req r = {0, 0, 0, 0};
+    u32 idx = (u32)e;
+    if (mine) {
+        longlong2 a = reinterpret_cast<const longlong2 *>(drec + idx)[0];
+        longlong2 b = reinterpret_cast<const longlong2 *>(drec + idx)[1];
+        r.now = a.x; r.ei = a.y; r.dvt = b.x; r.q = b.y;
+    }
+    // run heads read the entry; the run's lanes get it by shuffle
+    RunState s = {0, EXP_EMPTY, 0};
+    if (head) {
+        const Line *l = t.lines + (slot >> 2);
+        const u32 j = slot & 3;
+        s.tat = l->tat[j];
+        s.exp = (i64)((u64)s.tat + l->off[j]);
+        s.ei = l->ei[j];
+    }
+    s.tat = __shfl_sync(0xffffffffu, s.tat, hl);
+    s.exp = __shfl_sync(0xffffffffu, s.exp, hl);
+    s.ei = __shfl_sync(0xffffffffu, s.ei, hl);
+    const bool was_phantom = s.exp == EXP_PHANTOM;   // same for every lane of the run
+
+    Decision fin;
+    bool changed = false;
+    u32 exp_hits = 0;
+    run_chunk(lane, mine, gmask, r, s, fin, changed, exp_hits);
+
+    u32 n_allowed = 0, n_denied = 0;
+    if (mine) {
+        Outputs o = outputs_of(fin, r);
+        write_result(out + idx, o.remaining, o.reset_after, o.retry_after, 0, fin.allowed ? 1 : 0);
+        n_allowed += fin.allowed ? 1 : 0;
+        n_denied += fin.allowed ? 0 : 1;
+    }
+    // run tails: last lane of each run inside this chunk
+    const u32 run_changed_mask = __ballot_sync(0xffffffffu, mine && changed);
+    bool run_changed = (run_changed_mask & gmask) != 0;
+    const u32 next_slot_in = __shfl_down_sync(0xffffffffu, slot, 1);
+    const u32 mine_mask = __ballot_sync(0xffffffffu, mine);
+    const bool next_mine = lane < 31 && ((mine_mask >> (lane + 1)) & 1);
+    const bool tail = mine && (!next_mine || next_slot_in != slot);
+    // does the last run continue past this chunk?
+    bool cont = false;
+    {
+        u32 nxt = (base + 32 < n) ? (u32)(sorted[base + 32] >> 32) : 0xffffffffu;
+        cont = mine && lane == 31 && nxt == slot;
+    }
+    cont = __shfl_sync(0xffffffffu, cont ? 1 : 0, 31) != 0;
+
+    u32 real_inc = 0;
+    if (tail && !(cont && lane == 31)) {
+        if (run_changed) {
+            Line *l = t.lines + (slot >> 2);
+            const u32 j = slot & 3;
+            l->tat[j] = s.tat;
+            l->off[j] = (u64)s.exp - (u64)s.tat;
+            l->ei[j] = s.ei;
+            if (was_phantom) real_inc++;
+        }
+    }
+
+    if (cont) {
+        // walk the rest of the run that started at lane 31's run
+        const u32 run_slot = __shfl_sync(0xffffffffu, slot, 31);
+        RunState cs;
+        cs.tat = __shfl_sync(0xffffffffu, s.tat, 31);
+        cs.exp = __shfl_sync(0xffffffffu, s.exp, 31);
+        cs.ei = __shfl_sync(0xffffffffu, s.ei, 31);
+        bool c_changed = __shfl_sync(0xffffffffu, run_changed ? 1 : 0, 31) != 0;
+        const bool c_phantom = __shfl_sync(0xffffffffu, was_phantom ? 1 : 0, 31) != 0;
+        u32 b2 = base + 32;
+        for (;;) {
+            u32 p2 = b2 + lane;
+            u64 e2 = p2 < n ? sorted[p2] : ~0ULL;
+            bool in_run = p2 < n && (u32)(e2 >> 32) == run_slot;
+            const u32 rm = __ballot_sync(0xffffffffu, in_run);   // prefix (sorted)
+            if (rm == 0) break;
+            Req r2 = {0, 0, 0, 0};
+            u32 idx2 = (u32)e2;
+            if (in_run) {
+                longlong2 a = reinterpret_cast<const longlong2 *>(drec + idx2)[0];
+                longlong2 b = reinterpret_cast<const longlong2 *>(drec + idx2)[1];
+                r2.now = a.x; r2.ei = a.y; r2.dvt = b.x; r2.q = b.y;
+            }
+            RunState s2 = cs;
+            Decision f2;
+            bool ch2 = false;
+            run_chunk(lane, in_run, rm, r2, s2, f2, ch2, exp_hits);
+            if (in_run) {
+                Outputs o = outputs_of(f2, r2);
+                write_result(out + idx2, o.remaining, o.reset_after, o.retry_after, 0, f2.allowed ? 1 : 0);
+                n_allowed += f2.allowed ? 1 : 0;
+                n_denied += f2.allowed ? 0 : 1;
+            }
+            c_changed |= __ballot_sync(0xffffffffu, in_run && ch2) != 0;
+            const int last = 31 - __clz(rm);
+            cs.tat = __shfl_sync(0xffffffffu, s2.tat, last);
+            cs.exp = __shfl_sync(0xffffffffu, s2.exp, last);
+            cs.ei = __shfl_sync(0xffffffffu, s2.ei, last);
+            if (rm != 0xffffffffu) break;
+            b2 += 32;
+        }
+        if (lane == 31 && c_changed) {
+            Line *l = t.lines + (run_slot >> 2);
+            const u32 j = run_slot & 3;
+            l->tat[j] = cs.tat;
+            l->off[j] = (u64)cs.exp - (u64)cs.tat;
+            l->ei[j] = cs.ei;
+            if (c_phantom) real_inc++;
+        }
+    }
+
+    // warp-aggregated counters
+    for (int o = 16; o > 0; o >>= 1) {
+        n_allowed += __shfl_xor_sync(0xffffffffu, n_allowed, o);
+        n_denied += __shfl_xor_sync(0xffffffffu, n_denied, o);
+        real_inc += __shfl_xor_sync(0xffffffffu, real_inc, o);
+        exp_hits += __shfl_xor_sync(0xffffffffu, exp_hits, o);
+    }
+    if (lane == 0) {
+        if (n_allowed) atomicAdd(&t.counters[C_ALLOWED], (u64)n_allowed);
+        if (n_denied) atomicAdd(&t.counters[C_DENIED], (u64)n_denied);
+        if (real_inc) atomicAdd(&t.counters[C_REAL], (u64)real_inc);
+        if (exp_hits) atomicAdd(&t.counters[C_EXPIRED_HITS], (u64)exp_hits);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: sweep -- retain(expiry > now)
+// ---------------------------------------------------------------------------------------------
+// Streams the tat and off sectors of every line (16 B per slot, 128-bit loads, L1 bypass) and
+// clears the slots whose expiry <= now.  Writes only where something is evicted.
+__device__ __forceinline__ ulonglong2 ld_stream(const void *p) {
+    ulonglong2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+    return v;
+}
+
+__global__ void __launch_bounds__(TILE_THREADS)
+sweep_kernel(Table t, u32 total_lines, i64 now) {
+    u32 removed_real = 0, removed_all = 0, removed_stash = 0;
+    const u32 stride = gridDim.x * TILE_THREADS;
+    for (u32 li = blockIdx.x * TILE_THREADS + threadIdx.x; li < total_lines; li += stride) {
+        Line *l = t.lines + li;
+        ulonglong2 t0 = ld_stream(&l->tat[0]), t1 = ld_stream(&l->tat[2]);
+        ulonglong2 o0 = ld_stream(&l->off[0]), o1 = ld_stream(&l->off[2]);
+        i64 ex[4] = {(i64)(t0.x + o0.x), (i64)(t0.y + o0.y), (i64)(t1.x + o1.x), (i64)(t1.y + o1.y)};
+        const bool stash = li >= t.nb_main;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (ex[j] != EXP_EMPTY && ex[j] <= now) {
+                l->key[j] = stash ? KEY_TOMB : KEY_EMPTY;
+                l->tat[j] = 0;
+                l->off[j] = (u64)EXP_EMPTY;
+                removed_all++;
+                if (ex[j] >= 0) removed_real++;
+                if (stash) removed_stash++;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        removed_real += __shfl_xor_sync(0xffffffffu, removed_real, o);
+        removed_all += __shfl_xor_sync(0xffffffffu, removed_all, o);
+        removed_stash += __shfl_xor_sync(0xffffffffu, removed_stash, o);
+    }
+    if ((threadIdx.x & 31) == 0 && removed_all) {
+        atomicAdd(&t.counters[C_OCCUPIED], (u64)(0 - (u64)removed_all));
+        atomicAdd(&t.counters[C_REAL], (u64)(0 - (u64)removed_real));
+        atomicAdd(&t.counters[C_SWEPT], (u64)removed_real);
+        if (removed_stash) atomicAdd(&t.counters[C_STASH], (u64)(0 - (u64)removed_stash));
+    }
+}
+
+// fill lines with the empty pattern (also resets an emptied stash)
+__global__ void __launch_bounds__(TILE_THREADS)
+clear_lines_kernel(Line *lines, u32 first, u32 count) {
+    const u32 stride = gridDim.x * TILE_THREADS;
+    for (u32 i = blockIdx.x * TILE_THREADS + threadIdx.x; i < count; i += stride) {
+        Line *l = lines + first + i;
+#pragma unroll
+        for (int j = 0; j < 4; j++) { l->key[j] = KEY_EMPTY; l->tat[j] = 0; l->off[j] = (u64)EXP_EMPTY; l->ei[j] = 0; }
+    }
+}
+
+// re-insert every entry of `src` into the (empty, larger) table `dst` -- HashMap growth
+__global__ void __launch_bounds__(TILE_THREADS)
+rehash_kernel(Table src, u32 src_lines, Table dst) {
+    const u32 stride = gridDim.x * TILE_THREADS;
+    for (u32 li = blockIdx.x * TILE_THREADS + threadIdx.x; li < src_lines; li += stride) {
+        const Line *l = src.lines + li;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            u64 k = l->key[j];
+            if (k < 2) continue;
+            i64 ex = (i64)((u64)l->tat[j] + l->off[j]);
+            if (ex < 0) continue;   // phantoms carry no state
+            bool fresh;
+            u32 s = find_or_claim(dst, k, fresh);
+            if (s == dst.null_slot) { atomicAdd(&dst.counters[C_INSERT_FAIL], 1ULL); continue; }
+            Line *d = dst.lines + (s >> 2);
+            d->tat[s & 3] = l->tat[j];
+            d->off[s & 3] = l->off[j];
+            d->ei[s & 3] = l->ei[j];
+            atomicAdd(&dst.counters[C_OCCUPIED], 1ULL);
+            atomicAdd(&dst.counters[C_REAL], 1ULL);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Store-trait single operations (core/store/mod.rs:85-133): one thread, results in `res`
+// ---------------------------------------------------------------------------------------------
+struct StoreOpResult { i64 value; int flag; int status; };
+
+// op: 0 get (adaptive_cleanup.rs:246-252), 1 cas (:221-244), 2 set_nx (:254-278),
+//     3 peek (entry as stored: res[0].value = tat, res[1].value = expiry)
+__device__ __forceinline__ i64 expiry_of(i64 now, u64 ttl) {
+    u64 e = (u64)now + ttl;
+    return (e < ttl || e > (u64)I64_MAX) ? I64_MAX : (i64)e;
+}
+
+__global__ void store_op_kernel(Table t, int op, u64 key, i64 a, i64 b, u64 ttl, i64 now,
+                                StoreOpResult *res) {
+    StoreOpResult r = {0, 0, 0};
+    if (op == 2) {
+        bool fresh;
+        u32 s = find_or_claim(t, key, fresh);
+        if (s == t.null_slot) {
+            r.status = GCRA_INTERNAL;
+        } else {
+            Line *l = t.lines + (s >> 2);
+            const u32 j = s & 3;
+            if (fresh) atomicAdd(&t.counters[C_OCCUPIED], 1ULL);
+            i64 ex = fresh ? EXP_PHANTOM : (i64)((u64)l->tat[j] + l->off[j]);
+            if (ex > now) {
+                r.flag = 0;                                  // live entry: :264-265
+            } else {
+                l->tat[j] = a;
+                l->off[j] = (u64)expiry_of(now, ttl) - (u64)a;
+                r.flag = 1;
+                atomicAdd(&t.counters[C_ALLOWED], 1ULL);     // one mutating op
+                if (ex < 0) atomicAdd(&t.counters[C_REAL], 1ULL);
+                else atomicAdd(&t.counters[C_EXPIRED_HITS], 1ULL);   // :267
+            }
+        }
+    } else {
+        u32 s = find_slot(t, key);
+        if (s != t.null_slot) {
+            Line *l = t.lines + (s >> 2);
+            const u32 j = s & 3;
+            i64 tat = l->tat[j];
+            i64 ex = (i64)((u64)tat + l->off[j]);
+            if (op == 3) {
+                if (ex >= 0) { r.flag = 1; r.value = tat; res[1].value = ex; }
+            } else if (ex > now) {
+                if (op == 0) { r.flag = 1; r.value = tat; }
+                else if (tat == a) {                         // :236-240
+                    l->tat[j] = b;
+                    l->off[j] = (u64)expiry_of(now, ttl) - (u64)b;
+                    r.flag = 1;
+                    atomicAdd(&t.counters[C_ALLOWED], 1ULL);
+                }
+            } else if (op == 1 && ex >= 0) {
+                atomicAdd(&t.counters[C_EXPIRED_HITS], 1ULL);        // :232-235
+            }
+        }
+    }
+    res[0] = r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: routing for the hash-sharded multi-GPU engine -- stable partition by owner shard
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ u32 owner_of(u64 key_hash, u32 n_shards) {
+    // bits independent of the in-table bucket choices (those use mix64's low/high words directly)
+    u64 m = mix64(key_hash ^ 0xA24BAED4963EE407ULL);
+    return (u32)(((m >> 32) * (u64)n_shards) >> 32);
+}
+
+constexpr int ROUTE_MAX_SHARDS = 16;
+
+__global__ void __launch_bounds__(TILE_THREADS)
+route_count_kernel(const gcra_request *__restrict__ req, u32 n, u32 n_shards, u32 num_tiles,
+                   u32 *__restrict__ tile_counts) {
+    __shared__ u32 c[ROUTE_MAX_SHARDS];
+    if (threadIdx.x < ROUTE_MAX_SHARDS) c[threadIdx.x] = 0;
+    __syncthreads();
+    u32 i = blockIdx.x * TILE_THREADS + threadIdx.x;
+    if (i < n) atomicAdd(&c[owner_of(req[i].key_hash, n_shards)], 1u);
+    __syncthreads();
+    if (threadIdx.x < n_shards) tile_counts[threadIdx.x * num_tiles + blockIdx.x] = c[threadIdx.x];
+}
+
+// single CTA: exclusive scan of tile_counts in (shard, tile) order; per-shard totals to counts
+__global__ void __launch_bounds__(TILE_THREADS)
+route_scan_kernel(u32 *__restrict__ tile_counts, u32 n_shards, u32 num_tiles, u32 *__restrict__ counts) {
+    __shared__ u32 part[TILE_THREADS];
+    __shared__ u32 carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (u32 s = 0; s < n_shards; s++) {
+        u32 shard_start = carry;
+        u32 *row = tile_counts + s * num_tiles;
+        for (u32 b = 0; b < num_tiles; b += TILE_THREADS) {
+            u32 i = b + threadIdx.x;
+            u32 v = i < num_tiles ? row[i] : 0;
+            part[threadIdx.x] = v;
+            __syncthreads();
+            for (u32 off = 1; off < TILE_THREADS; off <<= 1) {
+                u32 x = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+                __syncthreads();
+                part[threadIdx.x] += x;
+                __syncthreads();
+            }
+            if (i < num_tiles) row[i] = carry + part[threadIdx.x] - v;
+            __syncthreads();
+            if (threadIdx.x == 0) carry += part[TILE_THREADS - 1];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) counts[s] = carry - shard_start;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(TILE_THREADS)
+route_scatter_kernel(const gcra_request *__restrict__ req, u32 n, u32 n_shards, u32 num_tiles,
+                     const u32 *__restrict__ tile_offsets, gcra_request *__restrict__ out,
+                     u32 *__restrict__ src_index) {
+    constexpr int NW = TILE_THREADS / 32;
+    __shared__ u32 wc[NW][ROUTE_MAX_SHARDS];
+    const u32 w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < NW * ROUTE_MAX_SHARDS) (&wc[0][0])[threadIdx.x] = 0;
+    __syncthreads();
+    u32 i = blockIdx.x * TILE_THREADS + threadIdx.x;
+    bool valid = i < n;
+    u32 own = valid ? owner_of(req[i].key_hash, n_shards) : 0;
+    u32 peers = __match_any_sync(0xffffffffu, valid ? own : (0x80000000u | lane));
+    u32 rank = __popc(peers & ((1u << lane) - 1));
+    if (valid && rank == 0) wc[w][own] = __popc(peers);
+    __syncthreads();
+    if (threadIdx.x < n_shards) {
+        u32 acc = 0;
+        for (int x = 0; x < NW; x++) { u32 v = wc[x][threadIdx.x]; wc[x][threadIdx.x] = acc; acc += v; }
+    }
+    __syncthreads();
+    if (valid) {
+        u32 pos = tile_offsets[own * num_tiles + blockIdx.x] + wc[w][own] + rank;
+        const ulonglong2 *s = reinterpret_cast<const ulonglong2 *>(req + i);
+        ulonglong2 *d = reinterpret_cast<ulonglong2 *>(out + pos);
+        d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
+        src_index[pos] = i;
+    }
+}
+
+__global__ void __launch_bounds__(TILE_THREADS)
+route_unpermute_kernel(const gcra_result *__restrict__ routed, const u32 *__restrict__ src_index, u32 n,
+                       gcra_result *__restrict__ out) {
+    u32 i = blockIdx.x * TILE_THREADS + threadIdx.x;
+    if (i < n) {
+        const ulonglong2 *s = reinterpret_cast<const ulonglong2 *>(routed + i);
+        ulonglong2 *d = reinterpret_cast<ulonglong2 *>(out + src_index[i]);
+        d[0] = s[0]; d[1] = s[1];
+    }
+}
+
+}  // namespace gcra
