@@ -509,15 +509,17 @@ static int host_batch(gcra_engine *h, uint64_t n, const void *req, size_t rsz, b
     while (done < n) {
         uint32_t m = (uint32_t)std::min<uint64_t>(n - done, h->max_batch);
         const unsigned char *src = (const unsigned char *)req + done * rsz;
+        // like the reference's mutating ops, sweep (if the store's policy says so) BEFORE the work
+        // (adaptive_cleanup.rs:229,261), with the clock of the first request of the chunk
+        int64_t now_hint = compact ? now_batch : ((const gcra_request *)req)[done].now_ns;
+        int rc = apply_policy(h, now_hint);
+        if (rc) return rc;
         CK(cudaMemcpyAsync(h->d_req, src, (size_t)m * rsz, cudaMemcpyHostToDevice, h->stream));
-        int rc = launch_batch(h, m, h->d_req, compact, now_batch, h->d_res, h->stream, true);
+        rc = launch_batch(h, m, h->d_req, compact, now_batch, h->d_res, h->stream, true);
         if (rc) return rc;
         CK(cudaMemcpyAsync(res + done, h->d_res, (size_t)m * sizeof(gcra_result), cudaMemcpyDeviceToHost, h->stream));
         RC(refresh_counters(h, false));
         CK(cudaStreamSynchronize(h->stream));
-        int64_t now_hint = compact ? now_batch : ((const gcra_request *)req)[done + m - 1].now_ns;
-        rc = apply_policy(h, now_hint);
-        if (rc) return rc;
         done += m;
     }
     return GCRA_OK;
