@@ -59,6 +59,8 @@ struct gcra_engine {
     void *d_req = nullptr;
     gcra_result *d_res = nullptr;
     u32 *route_counts = nullptr;
+    LongRun *long_runs = nullptr;
+    u32 *long_count = nullptr;
     PolicyDerived *d_pol = nullptr;
     uint32_t npol = 0;
     StoreOpResult *d_op = nullptr, *h_op = nullptr;
@@ -306,8 +308,14 @@ static int launch_batch(gcra_engine *h, uint32_t n, const void *d_req, bool comp
     }
     if (timed) CK(cudaEventRecord(h->ev[2], st));
     const uint32_t warps = (n + 31) / 32;
+    CK(cudaMemsetAsync(h->long_count, 0, sizeof(u32), st));
     decide_kernel<<<(warps + TILE_THREADS / 32 - 1) / (TILE_THREADS / 32), TILE_THREADS, 0, st>>>(
-        h->tab, src, h->drec, n, d_res);
+        h->tab, src, h->drec, n, d_res, h->long_runs, h->long_count);
+    if (n >= LONG_RUN_MIN) {
+        // hot keys (runs of >= LONG_RUN_MIN requests): one CTA each, persistent over the work list
+        decide_long_kernel<<<148 * 2, LONG_THREADS, 0, st>>>(h->tab, src, h->drec, d_res, h->long_runs, h->long_count);
+        h->launches++;
+    }
     h->launches++;
     if (timed) { CK(cudaEventRecord(h->ev[3], st)); h->ev_valid = true; }
     CK(cudaGetLastError());
@@ -358,6 +366,8 @@ int32_t gcra_create(const gcra_config *cfg, gcra_engine **out) {
               cudaMalloc(&h->d_res, mb * sizeof(gcra_result)) == cudaSuccess &&
               cudaMalloc(&h->route_counts, (size_t)ROUTE_MAX_SHARDS * ((mb + TILE_THREADS - 1) / TILE_THREADS) * sizeof(u32)) == cudaSuccess &&
               cudaMalloc(&h->d_op, 2 * sizeof(StoreOpResult)) == cudaSuccess &&
+              cudaMalloc(&h->long_runs, (mb / LONG_RUN_MIN + 1) * sizeof(LongRun)) == cudaSuccess &&
+              cudaMalloc(&h->long_count, sizeof(u32)) == cudaSuccess &&
               cudaMallocHost(&h->h_op, 2 * sizeof(StoreOpResult)) == cudaSuccess &&
               cudaMallocHost(&h->h_counters, C_COUNT * sizeof(u64)) == cudaSuccess;
     if (!ok) return fail("scratch allocation", cudaGetLastError());
@@ -394,7 +404,7 @@ void gcra_destroy(gcra_engine *h) {
     }
     cudaFree(h->tab.lines); cudaFree(h->tab.counters);
     cudaFree(h->drec); cudaFree(h->keys_a); cudaFree(h->keys_b); cudaFree(h->hist); cudaFree(h->tot);
-    cudaFree(h->d_req); cudaFree(h->d_res); cudaFree(h->route_counts); cudaFree(h->d_pol); cudaFree(h->d_op);
+    cudaFree(h->d_req); cudaFree(h->d_res); cudaFree(h->route_counts); cudaFree(h->long_runs); cudaFree(h->long_count); cudaFree(h->d_pol); cudaFree(h->d_op);
     cudaFreeHost(h->h_op); cudaFreeHost(h->h_counters);
     cudaEventDestroy(h->ev_counters);
     for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]);

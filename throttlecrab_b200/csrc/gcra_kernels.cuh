@@ -318,44 +318,97 @@ __device__ __forceinline__ void run_chunk(u32 lane, bool mine, u32 gmask, const 
     changed_any = mflag;
 }
 
+// A run of LONG_RUN_MIN or more requests on one key (a hot key) is not walked by its warp: the warp
+// appends (first position, length) to a work list and decide_long_kernel gives it a whole CTA.
+constexpr u32 LONG_RUN_MIN = 512;
+constexpr int LONG_THREADS = 512;
+struct LongRun { u32 start, len; };
+
+__device__ __forceinline__ void load_req(const Req *__restrict__ drec, u32 idx, Req &r) {
+    longlong2 a = reinterpret_cast<const longlong2 *>(drec + idx)[0];
+    longlong2 b = reinterpret_cast<const longlong2 *>(drec + idx)[1];
+    r.now = a.x; r.ei = a.y; r.dvt = b.x; r.q = b.y;
+}
+
+// first position >= lo whose slot differs from run_slot; sorted[lo] is known to be in the run.
+// Warp-cooperative 32-ary search (all lanes call it; result uniform).
+__device__ __forceinline__ u32 run_end(const u64 *__restrict__ sorted, u32 n, u32 lo, u32 run_slot, u32 lane) {
+    u32 hi = n;   // sorted[hi] (if any) is outside the run
+    while (hi - lo > 1) {
+        u32 p = lo + (u32)(((u64)(hi - lo) * (lane + 1)) / 33);
+        bool in = (u32)(sorted[p] >> 32) == run_slot;    // lo <= p < hi <= n
+        u32 m = __ballot_sync(0xffffffffu, in);          // monotone: a prefix of lanes
+        int k = __popc(m);
+        u32 plo = __shfl_sync(0xffffffffu, p, k > 0 ? k - 1 : 0);
+        u32 phi = __shfl_sync(0xffffffffu, p, k < 32 ? k : 31);
+        if (k > 0) lo = plo;
+        if (k < 32) hi = phi;
+    }
+    return hi;
+}
+
+__device__ __forceinline__ void store_state(const Table &t, u32 slot, const RunState &s) {
+    Line *l = t.lines + (slot >> 2);
+    const u32 j = slot & 3;
+    l->tat[j] = s.tat;
+    l->off[j] = (u64)s.exp - (u64)s.tat;
+    l->ei[j] = s.ei;
+}
+
 __global__ void __launch_bounds__(TILE_THREADS)
 decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ drec, u32 n,
-              gcra_result *__restrict__ out) {
+              gcra_result *__restrict__ out, LongRun *__restrict__ long_runs, u32 *__restrict__ long_count) {
     const u32 lane = threadIdx.x & 31;
     const u32 warp_global = (blockIdx.x * TILE_THREADS + threadIdx.x) >> 5;
-    u32 base = warp_global * 32;
+    const u32 base = warp_global * 32;
     if (base >= n) return;   // whole warp
 
-    u32 pos = base + lane;
-    u64 e = pos < n ? sorted[pos] : ~0ULL;
-    u32 slot = (u32)(e >> 32);
-    bool valid = pos < n && slot != t.null_slot;
-    // slot of the element just before this chunk
-    u32 prev_last = base > 0 ? (u32)(sorted[base - 1] >> 32) : 0xffffffffu;
+    const u32 pos = base + lane;
+    const u64 e = pos < n ? sorted[pos] : ~0ULL;
+    const u32 slot = (u32)(e >> 32);
+    const bool valid = pos < n && slot != t.null_slot;
+    // slot of the element just before this chunk, and just after it
+    const u32 prev_last = base > 0 ? (u32)(sorted[base - 1] >> 32) : 0xffffffffu;
+    const u32 next_first = base + 32 < n ? (u32)(sorted[base + 32] >> 32) : 0xffffffffu;
     u32 prev = __shfl_up_sync(0xffffffffu, slot, 1);
     if (lane == 0) prev = prev_last;
     // lanes continuing a run that started in an earlier chunk belong to that chunk's warp
     const u32 slot0 = __shfl_sync(0xffffffffu, slot, 0);
-    const u32 same0 = __ballot_sync(0xffffffffu, valid && slot == slot0);
-    // sorted => same0 is a prefix of lanes
+    const u32 same0 = __ballot_sync(0xffffffffu, valid && slot == slot0);   // sorted => a prefix
     const u32 foreign = (base > 0 && slot0 == prev_last) ? same0 : 0;
     bool mine = valid && !((foreign >> lane) & 1);
-    bool head = mine && (slot != prev || (lane > 0 && ((foreign >> (lane - 1)) & 1)));
+    const bool head = mine && slot != prev;
     const u32 heads = __ballot_sync(0xffffffffu, head);
     const u32 le = (lane == 31) ? 0xffffffffu : ((2u << lane) - 1);
     const int hl = mine ? (31 - __clz(heads & le)) : (int)lane;
     const u32 gmask = __match_any_sync(0xffffffffu, mine ? hl : (int)(32 + lane));
 
-    Req r = {0, 0, 0, 0};
-    u32 idx = (u32)e;
-    if (mine) {
-        longlong2 a = reinterpret_cast<const longlong2 *>(drec + idx)[0];
-        longlong2 b = reinterpret_cast<const longlong2 *>(drec + idx)[1];
-        r.now = a.x; r.ei = a.y; r.dvt = b.x; r.q = b.y;
+    // does the chunk's last run continue past the chunk?  (uniform)
+    const u32 slot31 = __shfl_sync(0xffffffffu, slot, 31);
+    const bool mine31 = __shfl_sync(0xffffffffu, mine ? 1 : 0, 31) != 0;
+    bool cont = mine31 && next_first == slot31;
+    const u32 gmask31 = __shfl_sync(0xffffffffu, gmask, 31);
+    if (cont) {
+        const u32 run_start = base + (u32)(__ffs(gmask31) - 1);
+        const u32 end = run_end(sorted, n, base + 32, slot31, lane);
+        if (end - run_start >= LONG_RUN_MIN) {
+            // hot key: hand the whole run (including its lanes here) to decide_long_kernel
+            if (lane == 0) {
+                u32 w = atomicAdd(long_count, 1u);
+                long_runs[w].start = run_start;
+                long_runs[w].len = end - run_start;
+            }
+            if ((gmask31 >> lane) & 1) mine = false;
+            cont = false;
+        }
     }
+
+    Req r = {0, 0, 0, 0};
+    const u32 idx = (u32)e;
+    if (mine) load_req(drec, idx, r);
     // run heads read the entry; the run's lanes get it by shuffle
     RunState s = {0, EXP_EMPTY, 0};
-    if (head) {
+    if (head && mine) {
         const Line *l = t.lines + (slot >> 2);
         const u32 j = slot & 3;
         s.tat = l->tat[j];
@@ -379,36 +432,22 @@ decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ d
         n_allowed += fin.allowed ? 1 : 0;
         n_denied += fin.allowed ? 0 : 1;
     }
-    // run tails: last lane of each run inside this chunk
+    // run tails: last lane of each run inside this chunk writes the run's state back
     const u32 run_changed_mask = __ballot_sync(0xffffffffu, mine && changed);
-    bool run_changed = (run_changed_mask & gmask) != 0;
+    const bool run_changed = (run_changed_mask & gmask) != 0;
     const u32 next_slot_in = __shfl_down_sync(0xffffffffu, slot, 1);
     const u32 mine_mask = __ballot_sync(0xffffffffu, mine);
     const bool next_mine = lane < 31 && ((mine_mask >> (lane + 1)) & 1);
     const bool tail = mine && (!next_mine || next_slot_in != slot);
-    // does the last run continue past this chunk?
-    bool cont = false;
-    {
-        u32 nxt = (base + 32 < n) ? (u32)(sorted[base + 32] >> 32) : 0xffffffffu;
-        cont = mine && lane == 31 && nxt == slot;
-    }
-    cont = __shfl_sync(0xffffffffu, cont ? 1 : 0, 31) != 0;
 
     u32 real_inc = 0;
-    if (tail && !(cont && lane == 31)) {
-        if (run_changed) {
-            Line *l = t.lines + (slot >> 2);
-            const u32 j = slot & 3;
-            l->tat[j] = s.tat;
-            l->off[j] = (u64)s.exp - (u64)s.tat;
-            l->ei[j] = s.ei;
-            if (was_phantom) real_inc++;
-        }
+    if (tail && !(cont && lane == 31) && run_changed) {
+        store_state(t, slot, s);
+        if (was_phantom) real_inc++;
     }
 
     if (cont) {
-        // walk the rest of the run that started at lane 31's run
-        const u32 run_slot = __shfl_sync(0xffffffffu, slot, 31);
+        // walk the rest of lane 31's run (< LONG_RUN_MIN requests), next chunk prefetched
         RunState cs;
         cs.tat = __shfl_sync(0xffffffffu, s.tat, 31);
         cs.exp = __shfl_sync(0xffffffffu, s.exp, 31);
@@ -416,18 +455,22 @@ decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ d
         bool c_changed = __shfl_sync(0xffffffffu, run_changed ? 1 : 0, 31) != 0;
         const bool c_phantom = __shfl_sync(0xffffffffu, was_phantom ? 1 : 0, 31) != 0;
         u32 b2 = base + 32;
+        u64 e2 = b2 + lane < n ? sorted[b2 + lane] : ~0ULL;
+        bool in_run = (u32)(e2 >> 32) == slot31 && b2 + lane < n;
+        Req r2 = {0, 0, 0, 0};
+        if (in_run) load_req(drec, (u32)e2, r2);
         for (;;) {
-            u32 p2 = b2 + lane;
-            u64 e2 = p2 < n ? sorted[p2] : ~0ULL;
-            bool in_run = p2 < n && (u32)(e2 >> 32) == run_slot;
-            const u32 rm = __ballot_sync(0xffffffffu, in_run);   // prefix (sorted)
+            const u32 rm = __ballot_sync(0xffffffffu, in_run);   // a prefix (sorted)
             if (rm == 0) break;
-            Req r2 = {0, 0, 0, 0};
-            u32 idx2 = (u32)e2;
-            if (in_run) {
-                longlong2 a = reinterpret_cast<const longlong2 *>(drec + idx2)[0];
-                longlong2 b = reinterpret_cast<const longlong2 *>(drec + idx2)[1];
-                r2.now = a.x; r2.ei = a.y; r2.dvt = b.x; r2.q = b.y;
+            // prefetch the following chunk while this one is decided
+            const u32 b3 = b2 + 32;
+            u64 e3 = ~0ULL;
+            bool in3 = false;
+            Req r3 = {0, 0, 0, 0};
+            if (rm == 0xffffffffu) {
+                e3 = b3 + lane < n ? sorted[b3 + lane] : ~0ULL;
+                in3 = (u32)(e3 >> 32) == slot31 && b3 + lane < n;
+                if (in3) load_req(drec, (u32)e3, r3);
             }
             RunState s2 = cs;
             Decision f2;
@@ -435,7 +478,7 @@ decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ d
             run_chunk(lane, in_run, rm, r2, s2, f2, ch2, exp_hits);
             if (in_run) {
                 Outputs o = outputs_of(f2, r2);
-                write_result(out + idx2, o.remaining, o.reset_after, o.retry_after, 0, f2.allowed ? 1 : 0);
+                write_result(out + (u32)e2, o.remaining, o.reset_after, o.retry_after, 0, f2.allowed ? 1 : 0);
                 n_allowed += f2.allowed ? 1 : 0;
                 n_denied += f2.allowed ? 0 : 1;
             }
@@ -445,19 +488,112 @@ decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ d
             cs.exp = __shfl_sync(0xffffffffu, s2.exp, last);
             cs.ei = __shfl_sync(0xffffffffu, s2.ei, last);
             if (rm != 0xffffffffu) break;
-            b2 += 32;
+            b2 = b3; e2 = e3; in_run = in3; r2 = r3;
         }
         if (lane == 31 && c_changed) {
-            Line *l = t.lines + (run_slot >> 2);
-            const u32 j = run_slot & 3;
-            l->tat[j] = cs.tat;
-            l->off[j] = (u64)cs.exp - (u64)cs.tat;
-            l->ei[j] = cs.ei;
+            store_state(t, slot31, cs);
             if (c_phantom) real_inc++;
         }
     }
 
     // warp-aggregated counters
+    for (int o = 16; o > 0; o >>= 1) {
+        n_allowed += __shfl_xor_sync(0xffffffffu, n_allowed, o);
+        n_denied += __shfl_xor_sync(0xffffffffu, n_denied, o);
+        real_inc += __shfl_xor_sync(0xffffffffu, real_inc, o);
+        exp_hits += __shfl_xor_sync(0xffffffffu, exp_hits, o);
+    }
+    if (lane == 0) {
+        if (n_allowed) atomicAdd(&t.counters[C_ALLOWED], (u64)n_allowed);
+        if (n_denied) atomicAdd(&t.counters[C_DENIED], (u64)n_denied);
+        if (real_inc) atomicAdd(&t.counters[C_REAL], (u64)real_inc);
+        if (exp_hits) atomicAdd(&t.counters[C_EXPIRED_HITS], (u64)exp_hits);
+    }
+}
+
+// Hot keys: one CTA per long run.  The run is consumed in strides of LONG_THREADS requests; inside a
+// stride every thread evaluates its request against the run's current state and the CTA finds the
+// first state-changing request (warp + block min-reduction); everything up to it is final, its new
+// state is broadcast, the rest re-evaluates.  Same exactness argument as run_chunk, block-wide.
+__global__ void __launch_bounds__(LONG_THREADS)
+decide_long_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ drec,
+                   gcra_result *__restrict__ out, const LongRun *__restrict__ long_runs,
+                   u32 *__restrict__ long_count) {
+    constexpr int NW = LONG_THREADS / 32;
+    __shared__ u32 sm_first[2][NW];
+    __shared__ RunState sm_state;
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 count = *long_count;
+    u32 n_allowed = 0, n_denied = 0, exp_hits = 0, real_inc = 0;
+    u32 parity = 0;
+    for (u32 item = blockIdx.x; item < count; item += gridDim.x) {
+        const u32 start = long_runs[item].start, len = long_runs[item].len;
+        const u32 slot = (u32)(sorted[start] >> 32);
+        RunState s;
+        {
+            const Line *l = t.lines + (slot >> 2);
+            const u32 j = slot & 3;
+            s.tat = l->tat[j];
+            s.exp = (i64)((u64)s.tat + l->off[j]);
+            s.ei = l->ei[j];
+        }
+        const bool was_phantom = s.exp == EXP_PHANTOM;
+        bool changed = false;
+        // software pipeline: the next stride's request is loaded while this one is decided
+        u32 p = start + tid;
+        bool active = tid < len;
+        u32 idx = 0;
+        Req r = {0, 0, 0, 0};
+        if (active) { idx = (u32)sorted[p]; load_req(drec, idx, r); }
+        for (u32 off = 0; off < len; off += LONG_THREADS) {
+            const u32 noff = off + LONG_THREADS;
+            const bool nactive = noff + tid < len;
+            u32 nidx = 0;
+            Req nr = {0, 0, 0, 0};
+            if (nactive) { nidx = (u32)sorted[start + noff + tid]; load_req(drec, nidx, nr); }
+            bool pending = active;
+            Decision fin;
+            for (;;) {
+                Decision d;
+                bool mut = false;
+                RunState so = s;
+                if (pending) {
+                    d = decide(s.tat, s.exp, r);
+                    if (d.allowed) {
+                        so.tat = d.new_tat; so.exp = d.new_exp; so.ei = r.ei;
+                        mut = (so.tat != s.tat) | (so.exp != s.exp) | (so.ei != s.ei);
+                    }
+                }
+                const u32 wmin = __reduce_min_sync(0xffffffffu, (pending && mut) ? tid : 0xffffffffu);
+                if (lane == 0) sm_first[parity][warp] = wmin;
+                __syncthreads();
+                const u32 first = __reduce_min_sync(0xffffffffu, lane < NW ? sm_first[parity][lane] : 0xffffffffu);
+                parity ^= 1;
+                if (pending && tid <= first) {
+                    fin = d;
+                    if (d.allowed && !d.live && s.exp >= 0) exp_hits++;
+                    pending = false;
+                    if (tid == first) sm_state = so;
+                }
+                if (first == 0xffffffffu) break;       // uniform: nobody changes the state any more
+                __syncthreads();
+                s = sm_state;
+                changed = true;
+            }
+            if (active) {
+                Outputs o = outputs_of(fin, r);
+                write_result(out + idx, o.remaining, o.reset_after, o.retry_after, 0, fin.allowed ? 1 : 0);
+                n_allowed += fin.allowed ? 1 : 0;
+                n_denied += fin.allowed ? 0 : 1;
+            }
+            active = nactive; idx = nidx; r = nr;
+        }
+        if (tid == 0 && changed) {
+            store_state(t, slot, s);
+            if (was_phantom) real_inc++;
+        }
+        __syncthreads();   // sm_state / sm_first reuse by the next item
+    }
     for (int o = 16; o > 0; o >>= 1) {
         n_allowed += __shfl_xor_sync(0xffffffffu, n_allowed, o);
         n_denied += __shfl_xor_sync(0xffffffffu, n_denied, o);
