@@ -166,6 +166,8 @@ int32_t gcra_sync(gcra_engine *h);
 /* device time (ms) of the kernels of the most recent batch call, measured with CUDA events on
  * the launching stream: [0] total, [1] ingest (hash probe), [2] sort, [3] decide */
 int32_t gcra_last_kernel_ms(gcra_engine *h, float out[4]);
+/* device time (ms) of the most recent sweep kernel (CUDA events on the launching stream) */
+int32_t gcra_last_sweep_ms(gcra_engine *h, float *ms);
 /* number of kernels this handle has launched since creation */
 uint64_t gcra_launch_count(gcra_engine *h);
 

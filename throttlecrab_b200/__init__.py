@@ -190,6 +190,11 @@ class _GpuStore:
         self._check(self._L.gcra_last_kernel_ms(self._h, C.byref(out)))
         return [float(x) for x in out]
 
+    def last_sweep_ms(self):
+        ms = C.c_float()
+        self._check(self._L.gcra_last_sweep_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
     def launch_count(self):
         return int(self._L.gcra_launch_count(self._h))
 

@@ -91,6 +91,7 @@ SYMBOLS = {
     "gcra_peek": (_i32, [_vp, _u64, _pi64, _pi64, _pu8]),
     "gcra_sync": (_i32, [_vp]),
     "gcra_last_kernel_ms": (_i32, [_vp, C.POINTER(C.c_float * 4)]),
+    "gcra_last_sweep_ms": (_i32, [_vp, C.POINTER(C.c_float)]),
     "gcra_launch_count": (_u64, [_vp]),
     "gcra_owner_of": (_u32, [_u64, _u32]),
     "gcra_route_partition": (_i32, [_vp, _u64, _vp, _u32, _vp, _vp, _vp, _vp]),

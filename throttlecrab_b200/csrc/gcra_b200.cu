@@ -67,6 +67,8 @@ struct gcra_engine {
     u64 *h_counters = nullptr;       // pinned snapshot, refreshed after every batch
     cudaEvent_t ev_counters = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_sweep[2] = {nullptr, nullptr};
+    bool sweep_timed = false;
     bool ev_valid = false;
     uint64_t launches = 0;
     uint64_t occupied_ub = 0;        // host-side upper bound of claimed slots
@@ -133,7 +135,10 @@ static int do_sweep(gcra_engine *h, int64_t now_ns, uint64_t *removed) {
     RC(refresh_counters(h, true));
     uint64_t before = h->h_counters[C_SWEPT];
     uint32_t grid = std::min<uint32_t>((h->total_lines + TILE_THREADS - 1) / TILE_THREADS, 148 * 8);
+    CK(cudaEventRecord(h->ev_sweep[0], h->stream));
     sweep_kernel<<<grid, TILE_THREADS, 0, h->stream>>>(h->tab, h->total_lines, now_ns);
+    CK(cudaEventRecord(h->ev_sweep[1], h->stream));
+    h->sweep_timed = true;
     h->launches++;
     CK(cudaGetLastError());
     RC(refresh_counters(h, true));
@@ -374,6 +379,8 @@ int32_t gcra_create(const gcra_config *cfg, gcra_engine **out) {
     memset(h->h_counters, 0, C_COUNT * sizeof(u64));
     cudaEventCreateWithFlags(&h->ev_counters, cudaEventDisableTiming);
     for (int i = 0; i < 4; i++) cudaEventCreate(&h->ev[i]);
+    cudaEventCreate(&h->ev_sweep[0]);
+    cudaEventCreate(&h->ev_sweep[1]);
     // store policy, defaults as in the reference constructors
     h->kind = cfg->store_kind;
     __int128 created = cfg->created_ns;
@@ -408,6 +415,7 @@ void gcra_destroy(gcra_engine *h) {
     cudaFreeHost(h->h_op); cudaFreeHost(h->h_counters);
     cudaEventDestroy(h->ev_counters);
     for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]);
+    cudaEventDestroy(h->ev_sweep[0]); cudaEventDestroy(h->ev_sweep[1]);
     cudaStreamDestroy(h->stream); cudaStreamDestroy(h->in_stream); cudaStreamDestroy(h->out_stream);
     delete h;
 }
@@ -693,6 +701,13 @@ int32_t gcra_last_kernel_ms(gcra_engine *h, float out[4]) {
     CK(cudaEventElapsedTime(&out[1], h->ev[0], h->ev[1]));
     CK(cudaEventElapsedTime(&out[2], h->ev[1], h->ev[2]));
     CK(cudaEventElapsedTime(&out[3], h->ev[2], h->ev[3]));
+    return GCRA_OK;
+}
+
+int32_t gcra_last_sweep_ms(gcra_engine *h, float *ms) {
+    if (!h->sweep_timed) { h->err = "no sweep yet"; return GCRA_INTERNAL; }
+    CK(cudaEventSynchronize(h->ev_sweep[1]));
+    CK(cudaEventElapsedTime(ms, h->ev_sweep[0], h->ev_sweep[1]));
     return GCRA_OK;
 }
 
