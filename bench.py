@@ -213,7 +213,9 @@ def main():
 
     d_req = torch.from_numpy(ticks.view(np.uint8).reshape(W + K, TICK * 48)).to(dev)
     d_res = torch.empty((W + K, TICK * 32), dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream(dev)
+    # an explicit (non-default) stream: handle 0 would mean "the engine's own stream" to the C ABI
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
 
     def step(i):
         if world == 1:
@@ -234,15 +236,19 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k1_ms = []
     torch.cuda.synchronize()
+    step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     ev0.record(stream)
+    step_ev[0].record(stream)
     for i in range(W, W + K):
         step(i)
+        step_ev[i - W + 1].record(stream)
     ev1.record(stream)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
     total_ms = ev0.elapsed_time(ev1)
     launches = store.launch_count() - launches0
+    step_ms = [step_ev[i].elapsed_time(step_ev[i + 1]) for i in range(K)]
     if dist:
         tmax = torch.tensor([total_ms], device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -310,7 +316,7 @@ def main():
     if world == 1:
         t_k1 = total_ms * 1e-3
         ach = alg_bytes / t_k1 / 1e9
-        roof = {"bound": "hbm", "kernel": "K1 = ingest + order + decide (11 launches per tick)",
+        roof = {"bound": "hbm", "kernel": "K1 = ingest + order + decide (13 launches per tick)",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_kind": peak_kind,
                 "traffic": None,
                 "algorithmic_bytes_per_decision": {"allowed": 112, "denied": 96},
@@ -328,6 +334,7 @@ def main():
                    "l2": "no flush: table %.2f GB and a distinct 80 MB tick per step exceed the 126 MB L2"
                          % (store.stats()["table_slots"] * 32 / 1e9),
                    "allowed_fraction": n_allowed / max(n_ok, 1), "gen_seconds": round(gen_s, 1)},
+        "step_ms": {"min": min(step_ms), "median": float(np.median(step_ms)), "max": max(step_ms)},
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(line), flush=True)

@@ -59,7 +59,7 @@ struct gcra_engine {
     void *d_req = nullptr;
     gcra_result *d_res = nullptr;
     u32 *route_counts = nullptr;
-    LongRun *long_runs = nullptr;
+    LongRun *long_runs = nullptr, *giant_runs = nullptr;
     u32 *long_count = nullptr;
     PolicyDerived *d_pol = nullptr;
     uint32_t npol = 0;
@@ -106,16 +106,17 @@ static void table_geometry(uint64_t capacity, uint32_t &total_lines, uint32_t &n
 static int alloc_table(gcra_engine *h, uint64_t capacity, Table &t, uint32_t &total_lines, u64 *counters) {
     uint32_t nb, ss;
     table_geometry(capacity, total_lines, nb, ss);
-    Line *lines = nullptr;
-    CK(cudaMalloc(&lines, (size_t)total_lines * sizeof(Line)));
-    t.lines = lines;
+    const size_t slots = (size_t)total_lines * 4;
+    CK(cudaMalloc(&t.keys, slots * sizeof(u64)));
+    CK(cudaMalloc(&t.state, slots * sizeof(TatOff)));
+    CK(cudaMalloc(&t.ei, slots * sizeof(i64)));
     t.nb_main = nb;
     t.stash_slots = ss;
     t.null_slot = total_lines * 4 - 1;
     t.slot_bits = ceil_log2((uint64_t)total_lines * 4);
     t.counters = counters;
-    uint32_t grid = std::min<uint32_t>((total_lines + TILE_THREADS - 1) / TILE_THREADS, 148 * 16);
-    clear_lines_kernel<<<grid, TILE_THREADS, 0, h->stream>>>(lines, 0, total_lines);
+    uint32_t grid = (uint32_t)std::min<size_t>((slots + TILE_THREADS - 1) / TILE_THREADS, 148 * 16);
+    clear_slots_kernel<<<grid, TILE_THREADS, 0, h->stream>>>(t, 0, slots);
     h->launches++;
     CK(cudaGetLastError());
     return GCRA_OK;
@@ -134,9 +135,9 @@ static int do_sweep(gcra_engine *h, int64_t now_ns, uint64_t *removed) {
     CK(cudaSetDevice(h->device));
     RC(refresh_counters(h, true));
     uint64_t before = h->h_counters[C_SWEPT];
-    uint32_t grid = std::min<uint32_t>((h->total_lines + TILE_THREADS - 1) / TILE_THREADS, 148 * 8);
+    uint32_t grid = (uint32_t)std::min<uint64_t>(((uint64_t)h->total_lines * 4 + TILE_THREADS * SWEEP_UNROLL - 1) / (TILE_THREADS * SWEEP_UNROLL), 148 * 16);
     CK(cudaEventRecord(h->ev_sweep[0], h->stream));
-    sweep_kernel<<<grid, TILE_THREADS, 0, h->stream>>>(h->tab, h->total_lines, now_ns);
+    sweep_kernel<<<grid, TILE_THREADS, 0, h->stream>>>(h->tab, (u64)h->total_lines * 4, now_ns);
     CK(cudaEventRecord(h->ev_sweep[1], h->stream));
     h->sweep_timed = true;
     h->launches++;
@@ -144,9 +145,9 @@ static int do_sweep(gcra_engine *h, int64_t now_ns, uint64_t *removed) {
     RC(refresh_counters(h, true));
     if (h->h_counters[C_STASH] == 0) {
         // no key lives in the stash any more: drop its tombstones
-        uint32_t ns = h->total_lines - h->tab.nb_main;
-        clear_lines_kernel<<<(ns + TILE_THREADS - 1) / TILE_THREADS, TILE_THREADS, 0, h->stream>>>(
-            h->tab.lines, h->tab.nb_main, ns);
+        uint64_t first = (uint64_t)h->tab.nb_main * 4, cnt = (uint64_t)h->total_lines * 4 - first;
+        clear_slots_kernel<<<(uint32_t)((cnt + TILE_THREADS - 1) / TILE_THREADS), TILE_THREADS, 0, h->stream>>>(
+            h->tab, first, cnt);
         h->launches++;
         CK(cudaGetLastError());
     }
@@ -169,7 +170,7 @@ static int grow(gcra_engine *h, uint64_t need) {
     int rc = alloc_table(h, newcap, nt, nl, ncounters);
     if (rc) return rc;
     uint32_t grid = std::min<uint32_t>((h->total_lines + TILE_THREADS - 1) / TILE_THREADS, 148 * 8);
-    rehash_kernel<<<grid, TILE_THREADS, 0, h->stream>>>(h->tab, h->total_lines, nt);
+    rehash_kernel<<<grid, TILE_THREADS, 0, h->stream>>>(h->tab, (u64)h->total_lines * 4, nt);
     h->launches++;
     CK(cudaGetLastError());
     // carry the running totals over
@@ -185,7 +186,7 @@ static int grow(gcra_engine *h, uint64_t need) {
     keep[C_STASH] = fresh[C_STASH];
     CK(cudaMemcpyAsync(ncounters, keep, sizeof(keep), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(h->tab.lines);
+    cudaFree(h->tab.keys); cudaFree(h->tab.state); cudaFree(h->tab.ei);
     cudaFree(h->tab.counters);
     h->tab = nt;
     h->total_lines = nl;
@@ -313,9 +314,14 @@ static int launch_batch(gcra_engine *h, uint32_t n, const void *d_req, bool comp
     }
     if (timed) CK(cudaEventRecord(h->ev[2], st));
     const uint32_t warps = (n + 31) / 32;
-    CK(cudaMemsetAsync(h->long_count, 0, sizeof(u32), st));
+    CK(cudaMemsetAsync(h->long_count, 0, 2 * sizeof(u32), st));
     decide_kernel<<<(warps + TILE_THREADS / 32 - 1) / (TILE_THREADS / 32), TILE_THREADS, 0, st>>>(
-        h->tab, src, h->drec, n, d_res, h->long_runs, h->long_count);
+        h->tab, src, h->drec, n, d_res, h->long_runs, h->giant_runs, h->long_count);
+    if (n >= GIANT_RUN_MIN) {
+        // hottest keys: one 8-CTA cluster per run, persistent over the work list
+        decide_giant_kernel<<<16 * CLUSTER_CTAS, LONG_THREADS, 0, st>>>(h->tab, src, h->drec, d_res, h->giant_runs, h->long_count);
+        h->launches++;
+    }
     if (n >= LONG_RUN_MIN) {
         // hot keys (runs of >= LONG_RUN_MIN requests): one CTA each, persistent over the work list
         decide_long_kernel<<<148 * 2, LONG_THREADS, 0, st>>>(h->tab, src, h->drec, d_res, h->long_runs, h->long_count);
@@ -372,7 +378,8 @@ int32_t gcra_create(const gcra_config *cfg, gcra_engine **out) {
               cudaMalloc(&h->route_counts, (size_t)ROUTE_MAX_SHARDS * ((mb + TILE_THREADS - 1) / TILE_THREADS) * sizeof(u32)) == cudaSuccess &&
               cudaMalloc(&h->d_op, 2 * sizeof(StoreOpResult)) == cudaSuccess &&
               cudaMalloc(&h->long_runs, (mb / LONG_RUN_MIN + 1) * sizeof(LongRun)) == cudaSuccess &&
-              cudaMalloc(&h->long_count, sizeof(u32)) == cudaSuccess &&
+              cudaMalloc(&h->giant_runs, (mb / GIANT_RUN_MIN + 1) * sizeof(LongRun)) == cudaSuccess &&
+              cudaMalloc(&h->long_count, 2 * sizeof(u32)) == cudaSuccess &&
               cudaMallocHost(&h->h_op, 2 * sizeof(StoreOpResult)) == cudaSuccess &&
               cudaMallocHost(&h->h_counters, C_COUNT * sizeof(u64)) == cudaSuccess;
     if (!ok) return fail("scratch allocation", cudaGetLastError());
@@ -409,9 +416,9 @@ void gcra_destroy(gcra_engine *h) {
         cudaFreeHost(s.h_req); cudaFreeHost(s.h_res); cudaFree(s.d_req); cudaFree(s.d_res);
         cudaEventDestroy(s.ev_in); cudaEventDestroy(s.ev_comp); cudaEventDestroy(s.ev_done);
     }
-    cudaFree(h->tab.lines); cudaFree(h->tab.counters);
+    cudaFree(h->tab.keys); cudaFree(h->tab.state); cudaFree(h->tab.ei); cudaFree(h->tab.counters);
     cudaFree(h->drec); cudaFree(h->keys_a); cudaFree(h->keys_b); cudaFree(h->hist); cudaFree(h->tot);
-    cudaFree(h->d_req); cudaFree(h->d_res); cudaFree(h->route_counts); cudaFree(h->long_runs); cudaFree(h->long_count); cudaFree(h->d_pol); cudaFree(h->d_op);
+    cudaFree(h->d_req); cudaFree(h->d_res); cudaFree(h->route_counts); cudaFree(h->long_runs); cudaFree(h->giant_runs); cudaFree(h->long_count); cudaFree(h->d_pol); cudaFree(h->d_op);
     cudaFreeHost(h->h_op); cudaFreeHost(h->h_counters);
     cudaEventDestroy(h->ev_counters);
     for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]);

@@ -19,15 +19,19 @@ constexpr i64 EXP_PHANTOM = -2;  // key claimed by a request that was denied: no
 constexpr i64 I64_MAX = 0x7fffffffffffffffLL;
 constexpr i64 I64_MIN = (-0x7fffffffffffffffLL - 1);
 
-// One bucket = one 128-byte line = four slots, structure-of-arrays inside the line: each
-// column's four values are exactly one 32-byte DRAM sector, so a probe reads one sector,
-// a decision touches the key/tat/off sectors of ONE line, and the sweep streams the tat+off
-// sectors with 128-bit loads.  expiry = tat + off (wrapping u64); stored off = expiry - tat.
-struct __align__(128) Line {
-    u64 key[4];   // mixed key hash; 0 empty, 1 tombstone (stash only)
-    i64 tat[4];   // theoretical arrival time, ns
-    u64 off[4];   // burst offset: expiry - tat (wrapping)
-    i64 ei[4];    // emission interval of the last write, ns
+// Structure of arrays, one element per slot; a bucket = 4 consecutive slots:
+//   keys[slot]   u64   mixed key hash (0 empty, 1 stash tombstone); a bucket's four keys are one
+//                      32-byte sector, compared after two 128-bit loads
+//   state[slot]  16 B  (tat_ns, burst_offset) -- always read and written together, so one decision is
+//                      ONE 128-bit load + ONE 128-bit store, and the sweep streams this array densely
+//                      (16 B per slot, coalesced 128-bit loads).  expiry = tat + off (wrapping).
+//   ei[slot]     i64   emission interval (ns) of the request that created the entry (informational)
+// Layout history (profiles/r01_k1_summary.md): v1 kept all four columns of a bucket in one 128-byte
+// line; ncu showed 64-byte DRAM fetch granules and a 44-54 %-of-peak sweep, and the probe (ingest
+// kernel) and the state update (decide kernel) touch their sectors in different kernels anyway.
+struct __align__(16) TatOff {
+    i64 tat;   // theoretical arrival time, ns
+    u64 off;   // burst offset: expiry - tat (wrapping)
 };
 
 enum Counter {
@@ -44,7 +48,9 @@ enum Counter {
 };
 
 struct Table {
-    Line *lines;      // nb_main bucket lines followed by the stash lines
+    u64 *keys;        // [slots]   main buckets (nb_main * 4 slots) followed by the stash slots
+    TatOff *state;    // [slots]
+    i64 *ei;          // [slots]
     u32 nb_main;      // buckets addressed by the two hash choices
     u32 stash_slots;  // slots probed linearly when both buckets are full
     u32 null_slot;    // reserved id: "this request has no slot" (last slot of the allocation)
@@ -163,10 +169,10 @@ __device__ __forceinline__ void bucket_choices(const Table &t, u64 k, u32 &b1, u
     if (b2 == b1) { b2 = b1 + 1; if (b2 == t.nb_main) b2 = 0; }
 }
 
-__device__ __forceinline__ void load_keys(const Line *l, u64 k[4]) {
+__device__ __forceinline__ void load_keys(const u64 *bucket, u64 k[4]) {
     // L2-coherent 128-bit loads: other CTAs claim slots with CAS during the same kernel
-    ulonglong2 a = __ldcg(reinterpret_cast<const ulonglong2 *>(&l->key[0]));
-    ulonglong2 b = __ldcg(reinterpret_cast<const ulonglong2 *>(&l->key[2]));
+    ulonglong2 a = __ldcg(reinterpret_cast<const ulonglong2 *>(bucket));
+    ulonglong2 b = __ldcg(reinterpret_cast<const ulonglong2 *>(bucket + 2));
     k[0] = a.x; k[1] = a.y; k[2] = b.x; k[3] = b.y;
 }
 
@@ -179,17 +185,17 @@ __device__ __forceinline__ u32 find_slot(const Table &t, u64 k) {
     u32 b1, b2;
     bucket_choices(t, k, b1, b2);
     u64 kk[4];
-    load_keys(t.lines + b1, kk);
+    load_keys(t.keys + (size_t)b1 * 4, kk);
 #pragma unroll
     for (int j = 0; j < 4; j++) if (kk[j] == k) return b1 * 4 + j;
-    load_keys(t.lines + b2, kk);
+    load_keys(t.keys + (size_t)b2 * 4, kk);
 #pragma unroll
     for (int j = 0; j < 4; j++) if (kk[j] == k) return b2 * 4 + j;
     if (__ldcg(&t.counters[C_STASH]) != 0) {
         u32 s = stash_start(t, k);
         for (u32 i = 0; i < t.stash_slots; i++) {
             u32 slot = t.nb_main * 4 + s;
-            u64 v = __ldcg(&t.lines[slot >> 2].key[slot & 3]);
+            u64 v = __ldcg(&t.keys[slot]);
             if (v == k) return slot;
             if (v == KEY_EMPTY) break;
             if (++s == t.stash_slots) s = 0;
@@ -203,7 +209,7 @@ __device__ __forceinline__ bool claim_in_bucket(const Table &t, u32 b, u64 kk[4]
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         if (kk[j] != KEY_EMPTY) continue;
-        u64 old = atomicCAS(&t.lines[b].key[j], KEY_EMPTY, k);
+        u64 old = atomicCAS(&t.keys[(size_t)b * 4 + j], KEY_EMPTY, k);
         if (old == KEY_EMPTY) { slot = b * 4 + j; fresh = true; return true; }
         if (old == k) { slot = b * 4 + j; fresh = false; return true; }
     }
@@ -218,10 +224,10 @@ __device__ __forceinline__ u32 find_or_claim(const Table &t, u64 k, bool &fresh)
     u32 b1, b2;
     bucket_choices(t, k, b1, b2);
     u64 k1[4], k2[4];
-    load_keys(t.lines + b1, k1);
+    load_keys(t.keys + (size_t)b1 * 4, k1);
 #pragma unroll
     for (int j = 0; j < 4; j++) if (k1[j] == k) return b1 * 4 + j;
-    load_keys(t.lines + b2, k2);
+    load_keys(t.keys + (size_t)b2 * 4, k2);
 #pragma unroll
     for (int j = 0; j < 4; j++) if (k2[j] == k) return b2 * 4 + j;
     // stash lookup (remember the first reusable stash slot on the way)
@@ -230,7 +236,7 @@ __device__ __forceinline__ u32 find_or_claim(const Table &t, u64 k, bool &fresh)
         u32 s = s0;
         for (u32 i = 0; i < t.stash_slots; i++) {
             u32 slot = t.nb_main * 4 + s;
-            u64 v = __ldcg(&t.lines[slot >> 2].key[slot & 3]);
+            u64 v = __ldcg(&t.keys[slot]);
             if (v == k) return slot;
             if (v == KEY_EMPTY) break;
             if (++s == t.stash_slots) s = 0;
@@ -243,7 +249,7 @@ __device__ __forceinline__ u32 find_or_claim(const Table &t, u64 k, bool &fresh)
     u32 s = s0;
     for (u32 i = 0; i < t.stash_slots; i++) {
         slot = t.nb_main * 4 + s;
-        u64 *p = &t.lines[slot >> 2].key[slot & 3];
+        u64 *p = &t.keys[slot];
         u64 v = __ldcg(p);
         while (v == KEY_EMPTY || v == KEY_TOMB) {
             u64 old = atomicCAS(p, v, k);

@@ -10,6 +10,8 @@
 //   K2  sweep   : HashMap::retain(expiry > now) (adaptive_cleanup.rs:176-182) as a streaming scan
 //   K3  route   : stable partition of a batch by owner shard for the multi-GPU all-to-all
 #pragma once
+#include <cooperative_groups.h>
+
 #include "gcra_device.cuh"
 #include "../../include/gcra_b200.h"
 
@@ -134,7 +136,7 @@ ingest_kernel(Table t, const void *__restrict__ req_base, const PolicyDerived *_
     if (in_range && status == 0) {
         slot = find_or_claim(t, stored_key(key_hash), fresh);
         if (slot == t.null_slot) status = GCRA_INTERNAL;   // table full
-        else if (fresh) t.lines[slot >> 2].off[slot & 3] = (u64)EXP_PHANTOM;
+        else if (fresh) t.state[slot].off = (u64)EXP_PHANTOM;
     }
     if (in_range) {
         reinterpret_cast<longlong2 *>(drec + i)[0] = make_longlong2(r.now, r.ei);
@@ -291,7 +293,7 @@ __device__ __forceinline__ void run_chunk(u32 lane, bool mine, u32 gmask, const 
             d = decide(s.tat, s.exp, r);
             if (d.allowed) {
                 so.tat = d.new_tat; so.exp = d.new_exp; so.ei = r.ei;
-                mut = (so.tat != s.tat) | (so.exp != s.exp) | (so.ei != s.ei);
+                mut = (so.tat != s.tat) | (so.exp != s.exp);
             }
         }
         const u32 P = __ballot_sync(0xffffffffu, pending);
@@ -320,8 +322,10 @@ __device__ __forceinline__ void run_chunk(u32 lane, bool mine, u32 gmask, const 
 
 // A run of LONG_RUN_MIN or more requests on one key (a hot key) is not walked by its warp: the warp
 // appends (first position, length) to a work list and decide_long_kernel gives it a whole CTA.
-constexpr u32 LONG_RUN_MIN = 512;
+constexpr u32 LONG_RUN_MIN = 512;     // >= this: one CTA per run (decide_long_kernel)
+constexpr u32 GIANT_RUN_MIN = 4096;   // >= this: one 8-CTA cluster per run (decide_giant_kernel)
 constexpr int LONG_THREADS = 512;
+constexpr int CLUSTER_CTAS = 8;
 struct LongRun { u32 start, len; };
 
 __device__ __forceinline__ void load_req(const Req *__restrict__ drec, u32 idx, Req &r) {
@@ -347,17 +351,23 @@ __device__ __forceinline__ u32 run_end(const u64 *__restrict__ sorted, u32 n, u3
     return hi;
 }
 
-__device__ __forceinline__ void store_state(const Table &t, u32 slot, const RunState &s) {
-    Line *l = t.lines + (slot >> 2);
-    const u32 j = slot & 3;
-    l->tat[j] = s.tat;
-    l->off[j] = (u64)s.exp - (u64)s.tat;
-    l->ei[j] = s.ei;
+__device__ __forceinline__ void load_state(const Table &t, u32 slot, RunState &s) {
+    const longlong2 v = *reinterpret_cast<const longlong2 *>(&t.state[slot]);   // LDG.128
+    s.tat = v.x;
+    s.exp = (i64)((u64)v.x + (u64)v.y);
+    s.ei = 0;
+}
+
+__device__ __forceinline__ void store_state(const Table &t, u32 slot, const RunState &s, bool created) {
+    *reinterpret_cast<longlong2 *>(&t.state[slot]) =
+        make_longlong2(s.tat, (i64)((u64)s.exp - (u64)s.tat));                                 // STG.128
+    if (created) t.ei[slot] = s.ei;
 }
 
 __global__ void __launch_bounds__(TILE_THREADS)
 decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ drec, u32 n,
-              gcra_result *__restrict__ out, LongRun *__restrict__ long_runs, u32 *__restrict__ long_count) {
+              gcra_result *__restrict__ out, LongRun *__restrict__ long_runs, LongRun *__restrict__ giant_runs,
+              u32 *__restrict__ long_count) {
     const u32 lane = threadIdx.x & 31;
     const u32 warp_global = (blockIdx.x * TILE_THREADS + threadIdx.x) >> 5;
     const u32 base = warp_global * 32;
@@ -394,9 +404,11 @@ decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ d
         if (end - run_start >= LONG_RUN_MIN) {
             // hot key: hand the whole run (including its lanes here) to decide_long_kernel
             if (lane == 0) {
-                u32 w = atomicAdd(long_count, 1u);
-                long_runs[w].start = run_start;
-                long_runs[w].len = end - run_start;
+                const bool giant = end - run_start >= GIANT_RUN_MIN;
+                u32 w = atomicAdd(long_count + (giant ? 1 : 0), 1u);
+                LongRun *dst = giant ? giant_runs : long_runs;
+                dst[w].start = run_start;
+                dst[w].len = end - run_start;
             }
             if ((gmask31 >> lane) & 1) mine = false;
             cont = false;
@@ -408,13 +420,7 @@ decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ d
     if (mine) load_req(drec, idx, r);
     // run heads read the entry; the run's lanes get it by shuffle
     RunState s = {0, EXP_EMPTY, 0};
-    if (head && mine) {
-        const Line *l = t.lines + (slot >> 2);
-        const u32 j = slot & 3;
-        s.tat = l->tat[j];
-        s.exp = (i64)((u64)s.tat + l->off[j]);
-        s.ei = l->ei[j];
-    }
+    if (head && mine) load_state(t, slot, s);
     s.tat = __shfl_sync(0xffffffffu, s.tat, hl);
     s.exp = __shfl_sync(0xffffffffu, s.exp, hl);
     s.ei = __shfl_sync(0xffffffffu, s.ei, hl);
@@ -442,7 +448,7 @@ decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ d
 
     u32 real_inc = 0;
     if (tail && !(cont && lane == 31) && run_changed) {
-        store_state(t, slot, s);
+        store_state(t, slot, s, was_phantom);
         if (was_phantom) real_inc++;
     }
 
@@ -491,7 +497,7 @@ decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ d
             b2 = b3; e2 = e3; in_run = in3; r2 = r3;
         }
         if (lane == 31 && c_changed) {
-            store_state(t, slot31, cs);
+            store_state(t, slot31, cs, c_phantom);
             if (c_phantom) real_inc++;
         }
     }
@@ -530,13 +536,7 @@ decide_long_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restric
         const u32 start = long_runs[item].start, len = long_runs[item].len;
         const u32 slot = (u32)(sorted[start] >> 32);
         RunState s;
-        {
-            const Line *l = t.lines + (slot >> 2);
-            const u32 j = slot & 3;
-            s.tat = l->tat[j];
-            s.exp = (i64)((u64)s.tat + l->off[j]);
-            s.ei = l->ei[j];
-        }
+        load_state(t, slot, s);
         const bool was_phantom = s.exp == EXP_PHANTOM;
         bool changed = false;
         // software pipeline: the next stride's request is loaded while this one is decided
@@ -561,7 +561,7 @@ decide_long_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restric
                     d = decide(s.tat, s.exp, r);
                     if (d.allowed) {
                         so.tat = d.new_tat; so.exp = d.new_exp; so.ei = r.ei;
-                        mut = (so.tat != s.tat) | (so.exp != s.exp) | (so.ei != s.ei);
+                        mut = (so.tat != s.tat) | (so.exp != s.exp);
                     }
                 }
                 const u32 wmin = __reduce_min_sync(0xffffffffu, (pending && mut) ? tid : 0xffffffffu);
@@ -589,7 +589,7 @@ decide_long_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restric
             active = nactive; idx = nidx; r = nr;
         }
         if (tid == 0 && changed) {
-            store_state(t, slot, s);
+            store_state(t, slot, s, was_phantom);
             if (was_phantom) real_inc++;
         }
         __syncthreads();   // sm_state / sm_first reuse by the next item
@@ -608,38 +608,153 @@ decide_long_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restric
     }
 }
 
+// The hottest keys (runs of >= GIANT_RUN_MIN requests; 63 K for the top key of a 2^20-request Zipf
+// tick): one thread-block CLUSTER of 8 CTAs per run.  A stride is 8 x 512 requests; each CTA reduces
+// its first state-changing request, the eight per-CTA minima are exchanged through distributed
+// shared memory (one remote load per lane), and the winner stores its new state into every CTA's
+// shared memory with remote stores.  Two cluster barriers per state change, one per clean stride.
+__global__ void __cluster_dims__(CLUSTER_CTAS, 1, 1) __launch_bounds__(LONG_THREADS)
+decide_giant_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ drec,
+                    gcra_result *__restrict__ out, const LongRun *__restrict__ giant_runs,
+                    const u32 *__restrict__ long_count) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    constexpr int NW = LONG_THREADS / 32;
+    constexpr u32 STRIDE = CLUSTER_CTAS * LONG_THREADS;
+    __shared__ u32 sm_wmin[2][NW];
+    __shared__ u32 sm_cta_first[2];
+    __shared__ RunState sm_state[2];
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 rank = cluster.block_rank();
+    const u32 gpos = rank * LONG_THREADS + tid;          // position inside a stride
+    const u32 cluster_id = blockIdx.x / CLUSTER_CTAS, num_clusters = gridDim.x / CLUSTER_CTAS;
+    const u32 count = long_count[1];
+    u32 n_allowed = 0, n_denied = 0, exp_hits = 0, real_inc = 0;
+    u32 par = 0;
+    for (u32 item = cluster_id; item < count; item += num_clusters) {
+        const u32 start = giant_runs[item].start, len = giant_runs[item].len;
+        const u32 slot = (u32)(sorted[start] >> 32);
+        RunState s;
+        load_state(t, slot, s);
+        const bool was_phantom = s.exp == EXP_PHANTOM;
+        bool changed = false;
+        bool active = gpos < len;
+        u32 idx = 0;
+        Req r = {0, 0, 0, 0};
+        if (active) { idx = (u32)sorted[start + gpos]; load_req(drec, idx, r); }
+        for (u32 off = 0; off < len; off += STRIDE) {
+            const u32 noff = off + STRIDE;
+            const bool nactive = noff + gpos < len;
+            u32 nidx = 0;
+            Req nr = {0, 0, 0, 0};
+            if (nactive) { nidx = (u32)sorted[start + noff + gpos]; load_req(drec, nidx, nr); }
+            bool pending = active;
+            Decision fin;
+            for (;;) {
+                Decision d;
+                bool mut = false;
+                RunState so = s;
+                if (pending) {
+                    d = decide(s.tat, s.exp, r);
+                    if (d.allowed) {
+                        so.tat = d.new_tat; so.exp = d.new_exp; so.ei = r.ei;
+                        mut = (so.tat != s.tat) | (so.exp != s.exp);
+                    }
+                }
+                const u32 wmin = __reduce_min_sync(0xffffffffu, (pending && mut) ? gpos : 0xffffffffu);
+                if (lane == 0) sm_wmin[par][warp] = wmin;
+                __syncthreads();
+                if (warp == 0) {
+                    const u32 cmin = __reduce_min_sync(0xffffffffu, lane < NW ? sm_wmin[par][lane] : 0xffffffffu);
+                    if (lane == 0) sm_cta_first[par] = cmin;
+                }
+                cluster.sync();
+                u32 v = 0xffffffffu;
+                if (lane < CLUSTER_CTAS) v = *cluster.map_shared_rank(&sm_cta_first[par], lane);   // DSMEM load
+                const u32 first = __reduce_min_sync(0xffffffffu, v);
+                if (pending && gpos <= first) {
+                    fin = d;
+                    if (d.allowed && !d.live && s.exp >= 0) exp_hits++;
+                    pending = false;
+                    if (gpos == first) {
+                        for (int c = 0; c < CLUSTER_CTAS; c++) *cluster.map_shared_rank(&sm_state[par], c) = so;   // DSMEM stores
+                    }
+                }
+                if (first == 0xffffffffu) { par ^= 1; break; }   // uniform over the cluster
+                cluster.sync();
+                s = sm_state[par];
+                changed = true;
+                par ^= 1;
+            }
+            if (active) {
+                Outputs o = outputs_of(fin, r);
+                write_result(out + idx, o.remaining, o.reset_after, o.retry_after, 0, fin.allowed ? 1 : 0);
+                n_allowed += fin.allowed ? 1 : 0;
+                n_denied += fin.allowed ? 0 : 1;
+            }
+            active = nactive; idx = nidx; r = nr;
+        }
+        if (rank == 0 && tid == 0 && changed) {
+            store_state(t, slot, s, was_phantom);
+            if (was_phantom) real_inc++;
+        }
+    }
+    cluster.sync();   // nobody leaves while its shared memory may still be read remotely
+    for (int o = 16; o > 0; o >>= 1) {
+        n_allowed += __shfl_xor_sync(0xffffffffu, n_allowed, o);
+        n_denied += __shfl_xor_sync(0xffffffffu, n_denied, o);
+        real_inc += __shfl_xor_sync(0xffffffffu, real_inc, o);
+        exp_hits += __shfl_xor_sync(0xffffffffu, exp_hits, o);
+    }
+    if (lane == 0) {
+        if (n_allowed) atomicAdd(&t.counters[C_ALLOWED], (u64)n_allowed);
+        if (n_denied) atomicAdd(&t.counters[C_DENIED], (u64)n_denied);
+        if (real_inc) atomicAdd(&t.counters[C_REAL], (u64)real_inc);
+        if (exp_hits) atomicAdd(&t.counters[C_EXPIRED_HITS], (u64)exp_hits);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K2: sweep -- retain(expiry > now)
 // ---------------------------------------------------------------------------------------------
-// Streams the tat and off sectors of every line (16 B per slot, 128-bit loads, L1 bypass) and
-// clears the slots whose expiry <= now.  Writes only where something is evicted.
+// One thread per slot: a coalesced 128-bit load of the (tat, off) pair (the warp reads eight dense
+// 64-byte line halves per instruction, L1 bypass), expiry = tat + off, and only the slots whose
+// expiry <= now are touched again: pair reset to the empty pattern, key cleared.
 __device__ __forceinline__ ulonglong2 ld_stream(const void *p) {
     ulonglong2 v;
     asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
     return v;
 }
 
+constexpr int SWEEP_UNROLL = 4;
+
 __global__ void __launch_bounds__(TILE_THREADS)
-sweep_kernel(Table t, u32 total_lines, i64 now) {
+sweep_kernel(Table t, u64 total_slots, i64 now) {
     u32 removed_real = 0, removed_all = 0, removed_stash = 0;
-    const u32 stride = gridDim.x * TILE_THREADS;
-    for (u32 li = blockIdx.x * TILE_THREADS + threadIdx.x; li < total_lines; li += stride) {
-        Line *l = t.lines + li;
-        ulonglong2 t0 = ld_stream(&l->tat[0]), t1 = ld_stream(&l->tat[2]);
-        ulonglong2 o0 = ld_stream(&l->off[0]), o1 = ld_stream(&l->off[2]);
-        i64 ex[4] = {(i64)(t0.x + o0.x), (i64)(t0.y + o0.y), (i64)(t1.x + o1.x), (i64)(t1.y + o1.y)};
-        const bool stash = li >= t.nb_main;
+    const u64 stride = (u64)gridDim.x * TILE_THREADS;
+    u64 i = (u64)blockIdx.x * TILE_THREADS + threadIdx.x;
+    while (i < total_slots) {
+        ulonglong2 v[SWEEP_UNROLL];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if (ex[j] != EXP_EMPTY && ex[j] <= now) {
-                l->key[j] = stash ? KEY_TOMB : KEY_EMPTY;
-                l->tat[j] = 0;
-                l->off[j] = (u64)EXP_EMPTY;
+        for (int u = 0; u < SWEEP_UNROLL; u++) {
+            const u64 k = i + (u64)u * stride;
+            v[u] = make_ulonglong2(0, (u64)EXP_EMPTY);
+            if (k < total_slots) v[u] = ld_stream(&t.state[k]);
+        }
+#pragma unroll
+        for (int u = 0; u < SWEEP_UNROLL; u++) {
+            const u64 k = i + (u64)u * stride;
+            const i64 ex = (i64)(v[u].x + v[u].y);
+            if (ex != EXP_EMPTY && ex <= now) {
+                const bool stash = k >= (u64)t.nb_main * 4;
+                *reinterpret_cast<longlong2 *>(&t.state[k]) = make_longlong2(0, EXP_EMPTY);
+                t.keys[k] = stash ? KEY_TOMB : KEY_EMPTY;
                 removed_all++;
-                if (ex[j] >= 0) removed_real++;
+                if (ex >= 0) removed_real++;
                 if (stash) removed_stash++;
             }
         }
+        i += (u64)SWEEP_UNROLL * stride;
     }
     for (int o = 16; o > 0; o >>= 1) {
         removed_real += __shfl_xor_sync(0xffffffffu, removed_real, o);
@@ -654,39 +769,33 @@ sweep_kernel(Table t, u32 total_lines, i64 now) {
     }
 }
 
-// fill lines with the empty pattern (also resets an emptied stash)
+// fill slots [first, first+count) with the empty pattern (also resets an emptied stash)
 __global__ void __launch_bounds__(TILE_THREADS)
-clear_lines_kernel(Line *lines, u32 first, u32 count) {
-    const u32 stride = gridDim.x * TILE_THREADS;
-    for (u32 i = blockIdx.x * TILE_THREADS + threadIdx.x; i < count; i += stride) {
-        Line *l = lines + first + i;
-#pragma unroll
-        for (int j = 0; j < 4; j++) { l->key[j] = KEY_EMPTY; l->tat[j] = 0; l->off[j] = (u64)EXP_EMPTY; l->ei[j] = 0; }
+clear_slots_kernel(Table t, u64 first, u64 count) {
+    const u64 stride = (u64)gridDim.x * TILE_THREADS;
+    for (u64 i = (u64)blockIdx.x * TILE_THREADS + threadIdx.x; i < count; i += stride) {
+        t.keys[first + i] = KEY_EMPTY;
+        *reinterpret_cast<longlong2 *>(&t.state[first + i]) = make_longlong2(0, EXP_EMPTY);
+        t.ei[first + i] = 0;
     }
 }
 
 // re-insert every entry of `src` into the (empty, larger) table `dst` -- HashMap growth
 __global__ void __launch_bounds__(TILE_THREADS)
-rehash_kernel(Table src, u32 src_lines, Table dst) {
-    const u32 stride = gridDim.x * TILE_THREADS;
-    for (u32 li = blockIdx.x * TILE_THREADS + threadIdx.x; li < src_lines; li += stride) {
-        const Line *l = src.lines + li;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            u64 k = l->key[j];
-            if (k < 2) continue;
-            i64 ex = (i64)((u64)l->tat[j] + l->off[j]);
-            if (ex < 0) continue;   // phantoms carry no state
-            bool fresh;
-            u32 s = find_or_claim(dst, k, fresh);
-            if (s == dst.null_slot) { atomicAdd(&dst.counters[C_INSERT_FAIL], 1ULL); continue; }
-            Line *d = dst.lines + (s >> 2);
-            d->tat[s & 3] = l->tat[j];
-            d->off[s & 3] = l->off[j];
-            d->ei[s & 3] = l->ei[j];
-            atomicAdd(&dst.counters[C_OCCUPIED], 1ULL);
-            atomicAdd(&dst.counters[C_REAL], 1ULL);
-        }
+rehash_kernel(Table src, u64 src_slots, Table dst) {
+    const u64 stride = (u64)gridDim.x * TILE_THREADS;
+    for (u64 i = (u64)blockIdx.x * TILE_THREADS + threadIdx.x; i < src_slots; i += stride) {
+        u64 k = src.keys[i];
+        if (k < 2) continue;
+        TatOff st = src.state[i];
+        if ((i64)((u64)st.tat + st.off) < 0) continue;   // phantoms carry no state
+        bool fresh;
+        u32 s = find_or_claim(dst, k, fresh);
+        if (s == dst.null_slot) { atomicAdd(&dst.counters[C_INSERT_FAIL], 1ULL); continue; }
+        dst.state[s] = st;
+        dst.ei[s] = src.ei[i];
+        atomicAdd(&dst.counters[C_OCCUPIED], 1ULL);
+        atomicAdd(&dst.counters[C_REAL], 1ULL);
     }
 }
 
@@ -711,15 +820,14 @@ __global__ void store_op_kernel(Table t, int op, u64 key, i64 a, i64 b, u64 ttl,
         if (s == t.null_slot) {
             r.status = GCRA_INTERNAL;
         } else {
-            Line *l = t.lines + (s >> 2);
-            const u32 j = s & 3;
+            TatOff *l = t.state + s;
             if (fresh) atomicAdd(&t.counters[C_OCCUPIED], 1ULL);
-            i64 ex = fresh ? EXP_PHANTOM : (i64)((u64)l->tat[j] + l->off[j]);
+            i64 ex = fresh ? EXP_PHANTOM : (i64)((u64)l->tat + l->off);
             if (ex > now) {
                 r.flag = 0;                                  // live entry: :264-265
             } else {
-                l->tat[j] = a;
-                l->off[j] = (u64)expiry_of(now, ttl) - (u64)a;
+                l->tat = a;
+                l->off = (u64)expiry_of(now, ttl) - (u64)a;
                 r.flag = 1;
                 atomicAdd(&t.counters[C_ALLOWED], 1ULL);     // one mutating op
                 if (ex < 0) atomicAdd(&t.counters[C_REAL], 1ULL);
@@ -729,17 +837,16 @@ __global__ void store_op_kernel(Table t, int op, u64 key, i64 a, i64 b, u64 ttl,
     } else {
         u32 s = find_slot(t, key);
         if (s != t.null_slot) {
-            Line *l = t.lines + (s >> 2);
-            const u32 j = s & 3;
-            i64 tat = l->tat[j];
-            i64 ex = (i64)((u64)tat + l->off[j]);
+            TatOff *l = t.state + s;
+            i64 tat = l->tat;
+            i64 ex = (i64)((u64)tat + l->off);
             if (op == 3) {
                 if (ex >= 0) { r.flag = 1; r.value = tat; res[1].value = ex; }
             } else if (ex > now) {
                 if (op == 0) { r.flag = 1; r.value = tat; }
                 else if (tat == a) {                         // :236-240
-                    l->tat[j] = b;
-                    l->off[j] = (u64)expiry_of(now, ttl) - (u64)b;
+                    l->tat = b;
+                    l->off = (u64)expiry_of(now, ttl) - (u64)b;
                     r.flag = 1;
                     atomicAdd(&t.counters[C_ALLOWED], 1ULL);
                 }
