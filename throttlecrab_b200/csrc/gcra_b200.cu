@@ -279,6 +279,24 @@ static int apply_policy(gcra_engine *h, int64_t now_ns) {
     return GCRA_OK;
 }
 
+// the cluster kernel: cluster dimension given at launch (cudaLaunchKernelEx)
+static int launch_giant(gcra_engine *h, const u64 *src, gcra_result *d_res, cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(16 * CLUSTER_CTAS);
+    cfg.blockDim = dim3(LONG_THREADS);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CLUSTER_CTAS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, decide_runs_kernel<CLUSTER_CTAS>, h->tab, (const u64 *)src, (const Req *)h->drec, d_res,
+                          (const LongRun *)h->giant_runs, (const u32 *)(h->long_count + 1)));
+    return GCRA_OK;
+}
+
 // ---- one batch on a stream -------------------------------------------------------------------
 static int launch_batch(gcra_engine *h, uint32_t n, const void *d_req, bool compact, int64_t now_batch,
                         gcra_result *d_res, cudaStream_t st, bool timed) {
@@ -319,12 +337,12 @@ static int launch_batch(gcra_engine *h, uint32_t n, const void *d_req, bool comp
         h->tab, src, h->drec, n, d_res, h->long_runs, h->giant_runs, h->long_count);
     if (n >= GIANT_RUN_MIN) {
         // hottest keys: one 8-CTA cluster per run, persistent over the work list
-        decide_giant_kernel<<<16 * CLUSTER_CTAS, LONG_THREADS, 0, st>>>(h->tab, src, h->drec, d_res, h->giant_runs, h->long_count);
+        RC(launch_giant(h, src, d_res, st));
         h->launches++;
     }
     if (n >= LONG_RUN_MIN) {
         // hot keys (runs of >= LONG_RUN_MIN requests): one CTA each, persistent over the work list
-        decide_long_kernel<<<148 * 2, LONG_THREADS, 0, st>>>(h->tab, src, h->drec, d_res, h->long_runs, h->long_count);
+        decide_runs_kernel<1><<<148, LONG_THREADS, 0, st>>>(h->tab, src, h->drec, d_res, h->long_runs, h->long_count);
         h->launches++;
     }
     h->launches++;

@@ -447,6 +447,8 @@ decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ d
     const bool tail = mine && (!next_mine || next_slot_in != slot);
 
     u32 real_inc = 0;
+    // informational ei column: emission interval of the run's first request in the creating batch
+    s.ei = __shfl_sync(0xffffffffu, r.ei, hl);
     if (tail && !(cont && lane == 31) && run_changed) {
         store_state(t, slot, s, was_phantom);
         if (was_phantom) real_inc++;
@@ -496,6 +498,7 @@ decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ d
             if (rm != 0xffffffffu) break;
             b2 = b3; e2 = e3; in_run = in3; r2 = r3;
         }
+        cs.ei = __shfl_sync(0xffffffffu, s.ei, 31);
         if (lane == 31 && c_changed) {
             store_state(t, slot31, cs, c_phantom);
             if (c_phantom) real_inc++;
@@ -517,127 +520,96 @@ decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ d
     }
 }
 
-// Hot keys: one CTA per long run.  The run is consumed in strides of LONG_THREADS requests; inside a
-// stride every thread evaluates its request against the run's current state and the CTA finds the
-// first state-changing request (warp + block min-reduction); everything up to it is final, its new
-// state is broadcast, the rest re-evaluates.  Same exactness argument as run_chunk, block-wide.
-__global__ void __launch_bounds__(LONG_THREADS)
-decide_long_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ drec,
-                   gcra_result *__restrict__ out, const LongRun *__restrict__ long_runs,
-                   u32 *__restrict__ long_count) {
-    constexpr int NW = LONG_THREADS / 32;
-    __shared__ u32 sm_first[2][NW];
-    __shared__ RunState sm_state;
-    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u32 count = *long_count;
-    u32 n_allowed = 0, n_denied = 0, exp_hits = 0, real_inc = 0;
-    u32 parity = 0;
-    for (u32 item = blockIdx.x; item < count; item += gridDim.x) {
-        const u32 start = long_runs[item].start, len = long_runs[item].len;
-        const u32 slot = (u32)(sorted[start] >> 32);
-        RunState s;
-        load_state(t, slot, s);
-        const bool was_phantom = s.exp == EXP_PHANTOM;
-        bool changed = false;
-        // software pipeline: the next stride's request is loaded while this one is decided
-        u32 p = start + tid;
-        bool active = tid < len;
-        u32 idx = 0;
-        Req r = {0, 0, 0, 0};
-        if (active) { idx = (u32)sorted[p]; load_req(drec, idx, r); }
-        for (u32 off = 0; off < len; off += LONG_THREADS) {
-            const u32 noff = off + LONG_THREADS;
-            const bool nactive = noff + tid < len;
-            u32 nidx = 0;
-            Req nr = {0, 0, 0, 0};
-            if (nactive) { nidx = (u32)sorted[start + noff + tid]; load_req(drec, nidx, nr); }
-            bool pending = active;
-            Decision fin;
-            for (;;) {
-                Decision d;
-                bool mut = false;
-                RunState so = s;
-                if (pending) {
-                    d = decide(s.tat, s.exp, r);
-                    if (d.allowed) {
-                        so.tat = d.new_tat; so.exp = d.new_exp; so.ei = r.ei;
-                        mut = (so.tat != s.tat) | (so.exp != s.exp);
-                    }
-                }
-                const u32 wmin = __reduce_min_sync(0xffffffffu, (pending && mut) ? tid : 0xffffffffu);
-                if (lane == 0) sm_first[parity][warp] = wmin;
-                __syncthreads();
-                const u32 first = __reduce_min_sync(0xffffffffu, lane < NW ? sm_first[parity][lane] : 0xffffffffu);
-                parity ^= 1;
-                if (pending && tid <= first) {
-                    fin = d;
-                    if (d.allowed && !d.live && s.exp >= 0) exp_hits++;
-                    pending = false;
-                    if (tid == first) sm_state = so;
-                }
-                if (first == 0xffffffffu) break;       // uniform: nobody changes the state any more
-                __syncthreads();
-                s = sm_state;
-                changed = true;
-            }
-            if (active) {
-                Outputs o = outputs_of(fin, r);
-                write_result(out + idx, o.remaining, o.reset_after, o.retry_after, 0, fin.allowed ? 1 : 0);
-                n_allowed += fin.allowed ? 1 : 0;
-                n_denied += fin.allowed ? 0 : 1;
-            }
-            active = nactive; idx = nidx; r = nr;
-        }
-        if (tid == 0 && changed) {
-            store_state(t, slot, s, was_phantom);
-            if (was_phantom) real_inc++;
-        }
-        __syncthreads();   // sm_state / sm_first reuse by the next item
+// ---------------------------------------------------------------------------------------------
+// Hot keys: runs of >= LONG_RUN_MIN requests get one CTA, runs of >= GIANT_RUN_MIN one 8-CTA cluster.
+// ---------------------------------------------------------------------------------------------
+// The run is consumed in strides (one request per thread of the group).  Two kinds of round:
+//
+//  * plain round: every pending thread evaluates its request against the run's current state; the
+//    group finds the first state-changing request (min-reduction); everything up to it is final and
+//    its new state becomes current.  One round per state change -- fine while changes are rare.
+//
+//  * finite-state round (after FSM_AFTER state changes in the run): some keys flip between a few
+//    states all the time (max_burst = 1: every zero-quantity request toggles the entry), which
+//    would cost one round per flip.  The threads keep the last K distinct states of the run as
+//    candidates, each request becomes a map "candidate in -> candidate out" (a nibble per candidate,
+//    0xF = leaves the candidate set), the maps are composed with an inclusive prefix scan (shuffles,
+//    shared memory, distributed shared memory across the cluster), and every request reads its TRUE
+//    input state off the scan.  A round is only repeated when a request creates a state that is not a
+//    candidate yet.  Still exact: each decision is decide(true input state, request).
+constexpr int FSM_K = 4;
+constexpr u32 FSM_NEW = 0xF;
+constexpr u32 FSM_IDENT = 0x3210;
+constexpr u32 FSM_AFTER = 4;
+
+__device__ __forceinline__ u32 fsm_compose(u32 f, u32 g) {   // first f, then g
+    const u64 gg = (u64)g | (0xFULL << 60);
+    u32 r = 0;
+#pragma unroll
+    for (int c = 0; c < FSM_K; c++) {
+        const u32 x = (f >> (4 * c)) & 0xF;
+        r |= ((u32)(gg >> (4 * x)) & 0xF) << (4 * c);
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        n_allowed += __shfl_xor_sync(0xffffffffu, n_allowed, o);
-        n_denied += __shfl_xor_sync(0xffffffffu, n_denied, o);
-        real_inc += __shfl_xor_sync(0xffffffffu, real_inc, o);
-        exp_hits += __shfl_xor_sync(0xffffffffu, exp_hits, o);
-    }
-    if (lane == 0) {
-        if (n_allowed) atomicAdd(&t.counters[C_ALLOWED], (u64)n_allowed);
-        if (n_denied) atomicAdd(&t.counters[C_DENIED], (u64)n_denied);
-        if (real_inc) atomicAdd(&t.counters[C_REAL], (u64)real_inc);
-        if (exp_hits) atomicAdd(&t.counters[C_EXPIRED_HITS], (u64)exp_hits);
-    }
+    return r;
 }
 
-// The hottest keys (runs of >= GIANT_RUN_MIN requests; 63 K for the top key of a 2^20-request Zipf
-// tick): one thread-block CLUSTER of 8 CTAs per run.  A stride is 8 x 512 requests; each CTA reduces
-// its first state-changing request, the eight per-CTA minima are exchanged through distributed
-// shared memory (one remote load per lane), and the winner stores its new state into every CTA's
-// shared memory with remote stores.  Two cluster barriers per state change, one per clean stride.
-__global__ void __cluster_dims__(CLUSTER_CTAS, 1, 1) __launch_bounds__(LONG_THREADS)
-decide_giant_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ drec,
-                    gcra_result *__restrict__ out, const LongRun *__restrict__ giant_runs,
-                    const u32 *__restrict__ long_count) {
+struct Cands {
+    i64 tat[FSM_K], exp[FSM_K];
+    __device__ __forceinline__ void get(u32 i, i64 &t, i64 &e) const {
+        t = tat[0]; e = exp[0];
+#pragma unroll
+        for (int c = 1; c < FSM_K; c++) if (i == (u32)c) { t = tat[c]; e = exp[c]; }
+    }
+    __device__ __forceinline__ void set(u32 i, i64 t, i64 e) {
+#pragma unroll
+        for (int c = 0; c < FSM_K; c++) if (i == (u32)c) { tat[c] = t; exp[c] = e; }
+    }
+    __device__ __forceinline__ u32 find(u32 nc, i64 t, i64 e) const {
+        u32 j = FSM_NEW;
+#pragma unroll
+        for (int c = 0; c < FSM_K; c++) if ((u32)c < nc && tat[c] == t && exp[c] == e) j = c;
+        return j;
+    }
+};
+
+struct PubState { i64 tat, exp; };
+
+template <int CTAS>
+__global__ void __launch_bounds__(LONG_THREADS, 1)
+decide_runs_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ drec,
+                   gcra_result *__restrict__ out, const LongRun *__restrict__ runs,
+                   const u32 *__restrict__ count_ptr) {
     namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
     constexpr int NW = LONG_THREADS / 32;
-    constexpr u32 STRIDE = CLUSTER_CTAS * LONG_THREADS;
-    __shared__ u32 sm_wmin[2][NW];
-    __shared__ u32 sm_cta_first[2];
-    __shared__ RunState sm_state[2];
+    constexpr u32 STRIDE = CTAS * LONG_THREADS;
+    __shared__ u32 sm_warp[2][NW];       // per-warp first-change position / composed map
+    __shared__ u32 sm_cta[2];            // this CTA's value, read by the other CTAs of the cluster
+    __shared__ PubState sm_pub[2];       // state created in this round (written into every CTA)
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u32 rank = cluster.block_rank();
+    u32 rank = 0, group_id = blockIdx.x, num_groups = gridDim.x;
+    if (CTAS > 1) {
+        rank = cg::this_cluster().block_rank();
+        group_id = blockIdx.x / CTAS;
+        num_groups = gridDim.x / CTAS;
+    }
+    auto group_sync = [&]() {
+        if (CTAS > 1) cg::this_cluster().sync(); else __syncthreads();
+    };
     const u32 gpos = rank * LONG_THREADS + tid;          // position inside a stride
-    const u32 cluster_id = blockIdx.x / CLUSTER_CTAS, num_clusters = gridDim.x / CLUSTER_CTAS;
-    const u32 count = long_count[1];
+    const u32 count = *count_ptr;
     u32 n_allowed = 0, n_denied = 0, exp_hits = 0, real_inc = 0;
     u32 par = 0;
-    for (u32 item = cluster_id; item < count; item += num_clusters) {
-        const u32 start = giant_runs[item].start, len = giant_runs[item].len;
+    for (u32 item = group_id; item < count; item += num_groups) {
+        const u32 start = runs[item].start, len = runs[item].len;
         const u32 slot = (u32)(sorted[start] >> 32);
-        RunState s;
-        load_state(t, slot, s);
-        const bool was_phantom = s.exp == EXP_PHANTOM;
-        bool changed = false;
+        RunState s0;
+        load_state(t, slot, s0);
+        const bool was_phantom = s0.exp == EXP_PHANTOM;
+        Cands cd;
+#pragma unroll
+        for (int c = 0; c < FSM_K; c++) { cd.tat[c] = s0.tat; cd.exp[c] = s0.exp; }
+        u32 nc = 1, cur = 0, victim = 0, n_changes = 0;
+        // software pipeline: the next stride's request is loaded while this one is decided
         bool active = gpos < len;
         u32 idx = 0;
         Req r = {0, 0, 0, 0};
@@ -649,57 +621,144 @@ decide_giant_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restri
             Req nr = {0, 0, 0, 0};
             if (nactive) { nidx = (u32)sorted[start + noff + gpos]; load_req(drec, nidx, nr); }
             bool pending = active;
-            Decision fin;
             for (;;) {
-                Decision d;
-                bool mut = false;
-                RunState so = s;
-                if (pending) {
-                    d = decide(s.tat, s.exp, r);
-                    if (d.allowed) {
-                        so.tat = d.new_tat; so.exp = d.new_exp; so.ei = r.ei;
-                        mut = (so.tat != s.tat) | (so.exp != s.exp);
+                const bool fsm = n_changes >= FSM_AFTER;
+                u32 in_idx = cur;            // candidate this thread's request really starts from
+                bool has_new;                // some request of this round created a new state
+                u32 total = FSM_IDENT;       // composed map of the whole round (fsm rounds)
+                u32 my_map = FSM_IDENT;
+                if (!fsm) {
+                    // ---- plain round: first state-changing request by min-reduction
+                    i64 ct, ce;
+                    cd.get(cur, ct, ce);
+                    bool mut = false;
+                    if (pending) {
+                        const Decision d = decide(ct, ce, r);
+                        mut = d.allowed && ((d.new_tat != ct) | (d.new_exp != ce));
                     }
+                    const u32 wmin = __reduce_min_sync(0xffffffffu, (pending && mut) ? gpos : 0xffffffffu);
+                    if (lane == 0) sm_warp[par][warp] = wmin;
+                    __syncthreads();
+                    u32 first = __reduce_min_sync(0xffffffffu, lane < NW ? sm_warp[par][lane] : 0xffffffffu);
+                    if (CTAS > 1) {
+                        if (tid == 0) sm_cta[par] = first;
+                        cg::this_cluster().sync();
+                        u32 v = 0xffffffffu;
+                        if (lane < CTAS) v = *cg::this_cluster().map_shared_rank(&sm_cta[par], lane);
+                        first = __reduce_min_sync(0xffffffffu, v);
+                    }
+                    has_new = first != 0xffffffffu;
+                    if (pending && gpos > first) in_idx = FSM_NEW;       // behind the change: retry
+                    if (pending && gpos == first) my_map = (FSM_IDENT & ~(0xFu << (4 * cur))) | (FSM_NEW << (4 * cur));
+                } else {
+                    // ---- finite-state round
+                    if (pending) {
+                        my_map = 0;
+#pragma unroll
+                        for (int c = 0; c < FSM_K; c++) {
+                            u32 o = FSM_NEW;
+                            if ((u32)c < nc) {
+                                const Decision d = decide(cd.tat[c], cd.exp[c], r);
+                                o = c;
+                                if (d.allowed && ((d.new_tat != cd.tat[c]) | (d.new_exp != cd.exp[c])))
+                                    o = cd.find(nc, d.new_tat, d.new_exp);
+                            }
+                            my_map |= o << (4 * c);
+                        }
+                    }
+                    u32 incl = my_map;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= (u32)d) incl = fsm_compose(o, incl);
+                    }
+                    u32 lane_excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                    if (lane == 0) lane_excl = FSM_IDENT;
+                    if (lane == 31) sm_warp[par][warp] = incl;
+                    __syncthreads();
+                    u32 wt = lane < NW ? sm_warp[par][lane] : FSM_IDENT;
+#pragma unroll
+                    for (int d = 1; d < NW; d <<= 1) {
+                        const u32 o = __shfl_up_sync(0xffffffffu, wt, d);
+                        if (lane >= (u32)d) wt = fsm_compose(o, wt);
+                    }
+                    u32 cta_total = __shfl_sync(0xffffffffu, wt, NW - 1);
+                    u32 excl = __shfl_sync(0xffffffffu, wt, warp > 0 ? warp - 1 : 0);
+                    if (warp == 0) excl = FSM_IDENT;
+                    total = cta_total;
+                    if (CTAS > 1) {
+                        if (tid == 0) sm_cta[par] = cta_total;
+                        cg::this_cluster().sync();
+                        u32 ctv = FSM_IDENT;
+                        if (lane < CTAS) ctv = *cg::this_cluster().map_shared_rank(&sm_cta[par], lane);
+#pragma unroll
+                        for (int d = 1; d < CTAS; d <<= 1) {
+                            const u32 o = __shfl_up_sync(0xffffffffu, ctv, d);
+                            if (lane >= (u32)d) ctv = fsm_compose(o, ctv);
+                        }
+                        total = __shfl_sync(0xffffffffu, ctv, CTAS - 1);
+                        u32 cexcl = __shfl_sync(0xffffffffu, ctv, rank > 0 ? rank - 1 : 0);
+                        if (rank == 0) cexcl = FSM_IDENT;
+                        excl = fsm_compose(cexcl, excl);
+                    }
+                    excl = fsm_compose(excl, lane_excl);
+                    in_idx = (excl >> (4 * cur)) & 0xF;
+                    has_new = ((total >> (4 * cur)) & 0xF) == FSM_NEW;
                 }
-                const u32 wmin = __reduce_min_sync(0xffffffffu, (pending && mut) ? gpos : 0xffffffffu);
-                if (lane == 0) sm_wmin[par][warp] = wmin;
-                __syncthreads();
-                if (warp == 0) {
-                    const u32 cmin = __reduce_min_sync(0xffffffffu, lane < NW ? sm_wmin[par][lane] : 0xffffffffu);
-                    if (lane == 0) sm_cta_first[par] = cmin;
-                }
-                cluster.sync();
-                u32 v = 0xffffffffu;
-                if (lane < CLUSTER_CTAS) v = *cluster.map_shared_rank(&sm_cta_first[par], lane);   // DSMEM load
-                const u32 first = __reduce_min_sync(0xffffffffu, v);
-                if (pending && gpos <= first) {
-                    fin = d;
-                    if (d.allowed && !d.live && s.exp >= 0) exp_hits++;
+                // ---- finalize every pending request whose true input state is known
+                if (pending && in_idx != FSM_NEW) {
+                    i64 ct, ce;
+                    cd.get(in_idx, ct, ce);
+                    const Decision d = decide(ct, ce, r);
+                    const Outputs o = outputs_of(d, r);
+                    write_result(out + idx, o.remaining, o.reset_after, o.retry_after, 0, d.allowed ? 1 : 0);
+                    n_allowed += d.allowed ? 1 : 0;
+                    n_denied += d.allowed ? 0 : 1;
+                    if (d.allowed && !d.live && ce >= 0) exp_hits++;
                     pending = false;
-                    if (gpos == first) {
-                        for (int c = 0; c < CLUSTER_CTAS; c++) *cluster.map_shared_rank(&sm_state[par], c) = so;   // DSMEM stores
+                    if (((my_map >> (4 * in_idx)) & 0xF) == FSM_NEW) {
+                        // this request created a state outside the candidate set: publish it
+                        PubState ps = {d.new_tat, d.new_exp};
+                        if (CTAS > 1) {
+                            for (int c = 0; c < CTAS; c++) *cg::this_cluster().map_shared_rank(&sm_pub[par], c) = ps;
+                        } else {
+                            sm_pub[par] = ps;
+                        }
                     }
                 }
-                if (first == 0xffffffffu) { par ^= 1; break; }   // uniform over the cluster
-                cluster.sync();
-                s = sm_state[par];
-                changed = true;
+                if (!has_new) {
+                    if (fsm) cur = (total >> (4 * cur)) & 0xF;
+                    par ^= 1;
+                    break;                                   // uniform over the group: stride done
+                }
+                group_sync();
+                const PubState ps = sm_pub[par];
                 par ^= 1;
-            }
-            if (active) {
-                Outputs o = outputs_of(fin, r);
-                write_result(out + idx, o.remaining, o.reset_after, o.retry_after, 0, fin.allowed ? 1 : 0);
-                n_allowed += fin.allowed ? 1 : 0;
-                n_denied += fin.allowed ? 0 : 1;
+                u32 v = cd.find(nc, ps.tat, ps.exp);          // plain rounds may return to a known state
+                if (v == FSM_NEW) {
+                    if (nc < FSM_K) { v = nc; nc++; }
+                    else { v = victim; victim = (victim + 1) % FSM_K; }
+                    cd.set(v, ps.tat, ps.exp);
+                }
+                cur = v;
+                n_changes++;
             }
             active = nactive; idx = nidx; r = nr;
         }
-        if (rank == 0 && tid == 0 && changed) {
-            store_state(t, slot, s, was_phantom);
-            if (was_phantom) real_inc++;
+        if (rank == 0 && tid == 0) {
+            RunState fs;
+            cd.get(cur, fs.tat, fs.exp);
+            if (fs.tat != s0.tat || fs.exp != s0.exp) {
+                Req first;
+                load_req(drec, (u32)sorted[start], first);
+                fs.ei = first.ei;
+                store_state(t, slot, fs, was_phantom);
+                if (was_phantom) real_inc++;
+            }
         }
+        __syncthreads();
     }
-    cluster.sync();   // nobody leaves while its shared memory may still be read remotely
+    if (CTAS > 1) cg::this_cluster().sync();   // nobody leaves while its shared memory may be accessed remotely
     for (int o = 16; o > 0; o >>= 1) {
         n_allowed += __shfl_xor_sync(0xffffffffu, n_allowed, o);
         n_denied += __shfl_xor_sync(0xffffffffu, n_denied, o);
