@@ -189,7 +189,7 @@ def main():
     t0 = time.time()
     key_hash_of = tc.hash_key_ids(np.arange(n_keys, dtype=np.uint64))
     store = tc.ManualStore(capacity=n_local_keys, device=local_rank, created_ns=traces.T0,
-                           max_batch=TICK + TICK // 4)
+                           max_batch=TICK if world == 1 else 2 * TICK)
     lim = tc.RateLimiter(store)
     if world == 1:
         # warm pass: every key inserted once (BASELINE configs[1]: keys resident)
@@ -203,10 +203,23 @@ def main():
     else:
         from throttlecrab_b200.sharded import ShardedLimiter
         sh = ShardedLimiter(lim, dist, dev)
-        # every rank generates its slice of each global tick; keys uniform over the global universe
-        tr = traces.config3(n_keys=n_keys, n_ticks=(W + K) * world, tick_size=TICK)
-        tr = tr.reshape(W + K, world, TICK)[:, rank, :].reshape(-1).copy()
-        tr["now_ns"] = traces.T0 + (np.arange(len(tr)) // TICK + 1) * 1_000_000
+        # warm pass through the sharded path: rank r submits keys [r*10M, (r+1)*10M), owners insert them
+        stream0 = torch.cuda.Stream(dev)
+        torch.cuda.set_stream(stream0)
+        wres = torch.empty(TICK * 32, dtype=torch.uint8, device=dev)
+        for a in range(0, n_local_keys, TICK):
+            ids = np.arange(rank * n_local_keys + a, rank * n_local_keys + min(a + TICK, n_local_keys), dtype=np.uint64)
+            w = np.zeros(TICK, traces.REQ_DTYPE)          # padded with copies of the last key (harmless)
+            w["key"][:len(ids)] = ids
+            w["key"][len(ids):] = ids[-1]
+            traces.fill_policy(w, (w["key"] % np.uint64(8)).astype(np.int64))
+            w["quantity"] = 1
+            w["now_ns"] = traces.T0
+            wreq = torch.from_numpy(build_requests(tc, key_hash_of, w).view(np.uint8)).to(dev)
+            sh.step(wreq, wres)
+        torch.cuda.synchronize()
+        # every rank generates ITS slice of each global Zipf tick (same generator as N=1)
+        tr = traces.config2_rank_slice(n_keys, TICK, 0, W + K, rank, world)
         ticks = build_requests(tc, key_hash_of, tr)
         del tr
     gen_s = time.time() - t0
@@ -221,11 +234,13 @@ def main():
         if world == 1:
             lim.rate_limit_batch_device(TICK, d_req[i].data_ptr(), d_res[i].data_ptr(), stream.cuda_stream)
         else:
-            sh.step(d_req[i], d_res[i])
+            sh.submit(d_req[i], d_res[i])       # pipelined: routing of tick i+1 overlaps deciding tick i
 
     # ---------------------------------------------------------------- kernel-only (value)
     for i in range(W):
         step(i)
+    if world > 1:
+        sh.finish()
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
@@ -242,6 +257,8 @@ def main():
     for i in range(W, W + K):
         step(i)
         step_ev[i - W + 1].record(stream)
+    if world > 1:
+        sh.finish()
     ev1.record(stream)
     torch.cuda.synchronize()
     if dist:
@@ -296,7 +313,76 @@ def main():
                "api": "gcra_ring_submit/gcra_ring_wait, pinned host ring, 48-byte requests",
                "matches_kernel_only_results": bool(same)}
         del ring
+        # extra: compact 16-byte requests (policy table + per-call now), same ticks, same results
+        ring16 = None
+        try:
+            store3 = tc.ManualStore(capacity=n_local_keys, device=local_rank, created_ns=traces.T0, max_batch=TICK)
+            lim3 = tc.RateLimiter(store3)
+            pol = np.zeros(8, tc.POLICY_DTYPE)
+            pol["max_burst"], pol["count_per_period"], pol["period"] = traces.POLICIES.T
+            lim3.set_policies(pol)
+            warm = build_requests(tc, key_hash_of, traces.warm_pass(n_keys))
+            for a in range(0, n_keys, TICK):
+                lim3.rate_limit_batch(warm[a:a + TICK])
+            del warm
+            ring16 = tc.Ring(lim3, slots=W + K, slot_capacity=TICK, compact=True)
+            for i in range(W + K):
+                sl = ticks[i * TICK:(i + 1) * TICK]
+                r16 = ring16.req[i]
+                r16["key_hash"] = sl["key_hash"]
+                r16["quantity"] = sl["quantity"]
+                pidx = np.zeros(TICK, np.uint32)
+                for j, p in enumerate(traces.POLICIES):
+                    m = (sl["max_burst"] == p[0]) & (sl["count_per_period"] == p[1]) & (sl["period"] == p[2])
+                    pidx[m] = j
+                r16["policy"] = pidx
+            nows = [int(ticks["now_ns"][i * TICK]) for i in range(W + K)]
+            for i in range(W):
+                ring16.submit(i, TICK, nows[i])
+            for i in range(W):
+                ring16.wait(i)
+            store3.sync()
+            t_a = time.perf_counter()
+            for i in range(W, W + K):
+                ring16.submit(i, TICK, nows[i])
+            for i in range(W, W + K):
+                ring16.wait(i)
+            t_b = time.perf_counter()
+            got16 = np.concatenate([ring16.res[i] for i in range(W, W + K)])
+            e2e["compact_requests"] = {"value": K * TICK / (t_b - t_a), "unit": UNIT, "h2d_bytes_per_step": TICK * 16,
+                                       "d2h_bytes_per_step": TICK * 32,
+                                       "matches_kernel_only_results": bool(got16.tobytes() == res_np.reshape(-1).tobytes())}
+            del ring16
+            store3.close()
+        except Exception as ex:      # the extra must never cost the main line
+            e2e["compact_requests"] = {"error": repr(ex)}
         store2.close()
+
+    if world > 1 and not args.no_e2e:
+        # e2e at N GPUs: every rank copies its tick slice from pinned host memory, routes, decides,
+        # routes back and copies the results to pinned host memory (time continues after the timed ticks)
+        tr2 = traces.config2_rank_slice(n_keys, TICK, W + K, K, rank, world)
+        h_req = torch.from_numpy(build_requests(tc, key_hash_of, tr2).view(np.uint8).reshape(K, TICK * 48)).pin_memory()
+        h_res = torch.empty((K, TICK * 32), dtype=torch.uint8).pin_memory()
+        torch.cuda.synchronize()
+        dist.barrier()
+        dqs = [torch.empty(TICK * 48, dtype=torch.uint8, device=dev) for _ in range(K)]
+        drs = [torch.empty(TICK * 32, dtype=torch.uint8, device=dev) for _ in range(K)]
+        t_a = time.perf_counter()
+        for i in range(K):
+            dqs[i].copy_(h_req[i], non_blocking=True)
+            sh.submit(dqs[i], drs[i])
+        sh.finish()
+        for i in range(K):
+            h_res[i].copy_(drs[i], non_blocking=True)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t_b = time.perf_counter()
+        tt = torch.tensor([t_b - t_a], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * K * TICK / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": TICK * 48,
+               "d2h_bytes_per_step": TICK * 32,
+               "api": "pinned host -> H2D -> ShardedLimiter.step (partition, all-to-all, decide, all-to-all) -> D2H, per rank"}
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N=1)
     cpu = None
@@ -328,8 +414,9 @@ def main():
         "dtype": "int64", "data": "synthetic",
         "config": {"workload": ("10M keys, Zipf-1.0 request stream, ticks of 2^20 requests (BASELINE configs[1])"
                                 if world == 1 else
-                                "%dM keys hash-sharded over %d GPUs, uniform stream, 2^20 requests per GPU per tick, "
-                                "NCCL all-to-all routing (BASELINE configs[4] shape)" % (n_keys // 1_000_000, world)),
+                                "%dM keys hash-sharded over %d GPUs, Zipf-1.0 stream, 2^20 requests per GPU per tick, "
+                                "stable partition + NCCL all-to-all routing (BASELINE configs[4] shape)"
+                                % (n_keys // 1_000_000, world)),
                    "keys": n_keys, "tick": TICK, "request_bytes": 48, "result_bytes": 32,
                    "l2": "no flush: table %.2f GB and a distinct 80 MB tick per step exceed the 126 MB L2"
                          % (store.stats()["table_slots"] * 32 / 1e9),

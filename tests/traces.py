@@ -98,11 +98,18 @@ def config1(n=100_000, keys=1000, policy_of_key=None):
     return req
 
 
+_CDF_CACHE = {}
+
+
 def zipf_ranks(u, n_keys, s=1.0):
     """Inverse-CDF Zipf(s) over ranks 1..n_keys on a harmonic table (float64 cumsum)."""
-    w = 1.0 / np.power(np.arange(1, n_keys + 1, dtype=np.float64), s)
-    cdf = np.cumsum(w)
-    cdf /= cdf[-1]
+    cdf = _CDF_CACHE.get((n_keys, s))
+    if cdf is None:
+        w = 1.0 / np.power(np.arange(1, n_keys + 1, dtype=np.float64), s)
+        cdf = np.cumsum(w)
+        cdf /= cdf[-1]
+        _CDF_CACHE.clear()
+        _CDF_CACHE[(n_keys, s)] = cdf
     return np.searchsorted(cdf, unit(u), side="left").astype(np.uint64)   # 0-based rank
 
 
@@ -161,3 +168,19 @@ def warm_pass(n_keys, now_ns=T0):
     req["quantity"] = 1
     req["now_ns"] = now_ns
     return req
+
+
+def config2_rank_slice(n_keys, tick_size, first_tick, n_ticks, rank, world):
+    """Rank `rank`'s slice of global Zipf ticks: global tick t has world*tick_size requests, rank r
+    owns rows [r*tick_size, (r+1)*tick_size) of it (global index order = rank order inside a tick)."""
+    out = np.zeros(n_ticks * tick_size, REQ_DTYPE)
+    for j in range(n_ticks):
+        t = first_tick + j
+        start = (t * world + rank) * tick_size
+        key = rank_to_key(zipf_ranks(stream(2, 0, tick_size, start), n_keys), n_keys)
+        sl = out[j * tick_size:(j + 1) * tick_size]
+        sl["key"] = key
+        fill_policy(sl, (key % np.uint64(8)).astype(np.int64))
+        sl["quantity"] = quantities(stream(2, 3, tick_size, start))
+        sl["now_ns"] = T0 + (t + 1) * 1_000_000
+    return out

@@ -9,16 +9,19 @@ results and gcra_route_unpermute puts them back in input order.
 Ordering rule: inside a tick, requests are applied in GLOBAL index order, where rank r's slice
 precedes rank r+1's.  The stable partition keeps slice order inside every group and all-to-all
 concatenates the groups in source-rank order, so the owner sees each key's requests in that order.
+Ticks are decided strictly in submission order on one stream.
 
-torch is plumbing only: device buffers, the NCCL process group and stream ordering.
+Pipelining: `submit()` only enqueues.  The route half of tick i+1 (partition, count exchange,
+request all-to-all) runs on its own stream while the decide half of tick i (kernels, result
+all-to-all, un-permutation) runs on another; the two halves of one tick are ordered by events.
+`DEPTH` buffer sets are cycled; `finish()` drains.  `step()` = submit + finish (blocking).
+
+torch is plumbing only: device buffers, the NCCL process group and stream/event ordering.
 """
-import ctypes as C
-
 import torch
 
-from . import _native
-
 REQ_B, RES_B = 48, 32
+DEPTH = 3
 
 
 class CudaOps:
@@ -43,43 +46,107 @@ class CudaOps:
                                                 res.data_ptr(), stream))
 
 
+class _Slot:
+    def __init__(self, max_rows, device):
+        u8 = dict(dtype=torch.uint8, device=device)
+        self.routed = torch.empty(max_rows * REQ_B, **u8)
+        self.recv_req = torch.empty(max_rows * REQ_B, **u8)
+        self.recv_res = torch.empty(max_rows * RES_B, **u8)
+        self.back_res = torch.empty(max_rows * RES_B, **u8)
+        self.src_index = torch.empty(max_rows, dtype=torch.int32, device=device)
+        self.counts = torch.zeros(16, dtype=torch.int32, device=device)
+        self.routed_ev = None      # request all-to-all finished
+        self.done_ev = None        # results un-permuted into the caller's buffer
+
+
 class ShardedLimiter:
     def __init__(self, limiter, dist, device, ops=None, max_rows=None):
         self.dist, self.dev = dist, device
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
         self.ops = ops if ops is not None else CudaOps(limiter)
         self.max_rows = max_rows or limiter.store.max_batch
-        u8 = dict(dtype=torch.uint8, device=device)
-        self.routed = torch.empty(self.max_rows * REQ_B, **u8)
-        self.recv_req = torch.empty(self.max_rows * REQ_B, **u8)
-        self.recv_res = torch.empty(self.max_rows * RES_B, **u8)
-        self.back_res = torch.empty(self.max_rows * RES_B, **u8)
-        self.src_index = torch.empty(self.max_rows, dtype=torch.int32, device=device)
-        self.counts = torch.zeros(16, dtype=torch.int32, device=device)
+        self.cuda = device.type == "cuda"
+        self.slots = [_Slot(self.max_rows, device) for _ in range(DEPTH if self.cuda else 1)]
+        self.n_submitted = 0
+        self.pending = None
         self.last_recv_rows = 0
+        if self.cuda:
+            self.s_route = torch.cuda.Stream(device)
+            self.s_decide = torch.cuda.Stream(device)
 
-    def _stream(self):
-        return torch.cuda.current_stream(self.dev).cuda_stream if self.dev.type == "cuda" else None
-
-    def step(self, d_req, d_res):
-        """d_req: uint8 tensor of n*48 bytes (gcra_request rows); d_res: uint8 tensor of n*32 bytes."""
-        n = d_req.numel() // REQ_B
-        W, dist, st = self.world, self.dist, self._stream()
-        self.ops.partition(n, d_req, W, self.routed, self.src_index, self.counts, st)
-        send = self.counts[:W].to(torch.int64)
+    # ------------------------------------------------------------------ the two halves of a tick
+    def _route(self, slot, d_req, n, stream):
+        W, dist = self.world, self.dist
+        self.ops.partition(n, d_req, W, slot.routed, slot.src_index, slot.counts, stream)
+        send = slot.counts[:W].to(torch.int64)
         recv = torch.empty_like(send)
         dist.all_to_all_single(recv, send)                       # how many rows every peer sends me
-        send_l, recv_l = send.tolist(), recv.tolist()            # one host sync per tick
+        send_l, recv_l = send.tolist(), recv.tolist()            # host sync of the ROUTE stream only
         n_recv = sum(recv_l)
         if n_recv > self.max_rows:
             raise RuntimeError("shard received %d rows > max_batch %d" % (n_recv, self.max_rows))
-        self.last_recv_rows = n_recv
-        dist.all_to_all_single(self.recv_req[:n_recv * REQ_B], self.routed[:n * REQ_B],
+        dist.all_to_all_single(slot.recv_req[:n_recv * REQ_B], slot.routed[:n * REQ_B],
                                output_split_sizes=[c * REQ_B for c in recv_l],
                                input_split_sizes=[c * REQ_B for c in send_l])
-        self.ops.decide(n_recv, self.recv_req, self.recv_res, st)
-        dist.all_to_all_single(self.back_res[:n * RES_B], self.recv_res[:n_recv * RES_B],
+        return send_l, recv_l, n_recv
+
+    def _decide(self, slot, d_res, n, send_l, recv_l, n_recv, stream):
+        dist = self.dist
+        self.ops.decide(n_recv, slot.recv_req, slot.recv_res, stream)
+        dist.all_to_all_single(slot.back_res[:n * RES_B], slot.recv_res[:n_recv * RES_B],
                                output_split_sizes=[c * RES_B for c in send_l],
                                input_split_sizes=[c * RES_B for c in recv_l])
-        self.ops.unpermute(n, self.back_res, self.src_index, d_res, st)
+        self.ops.unpermute(n, slot.back_res, slot.src_index, d_res, stream)
+
+    # ------------------------------------------------------------------ public
+    def submit(self, d_req, d_res):
+        """Enqueue one tick.  d_req: uint8 tensor of n*48 bytes (gcra_request rows), ready on the
+        caller's current stream; d_res: uint8 tensor of n*32 bytes, valid after finish()."""
+        n = d_req.numel() // REQ_B
+        slot = self.slots[self.n_submitted % len(self.slots)]
+        self.n_submitted += 1
+        if not self.cuda:
+            send_l, recv_l, n_recv = self._route(slot, d_req, n, None)
+            self._decide(slot, d_res, n, send_l, recv_l, n_recv, None)
+            self.last_recv_rows = n_recv
+            return n_recv
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(self.s_route):
+            self.s_route.wait_event(ready)
+            if slot.done_ev is not None:
+                self.s_route.wait_event(slot.done_ev)            # the slot's buffers are free again
+            send_l, recv_l, n_recv = self._route(slot, d_req, n, self.s_route.cuda_stream)
+            slot.routed_ev = torch.cuda.Event()
+            slot.routed_ev.record(self.s_route)
+        # NCCL runs the collectives of one communicator in issue order, so the decide half of the
+        # PREVIOUS tick is issued only now, after this tick's request all-to-all: the previous tick's
+        # kernels then overlap this tick's routing instead of blocking it.
+        self._issue_pending_decide()
+        self.pending = (slot, d_res, n, send_l, recv_l, n_recv)
+        self.last_recv_rows = n_recv
+        return n_recv
+
+    def _issue_pending_decide(self):
+        if self.pending is None:
+            return
+        slot, d_res, n, send_l, recv_l, n_recv = self.pending
+        self.pending = None
+        with torch.cuda.stream(self.s_decide):
+            self.s_decide.wait_event(slot.routed_ev)
+            self._decide(slot, d_res, n, send_l, recv_l, n_recv, self.s_decide.cuda_stream)
+            slot.done_ev = torch.cuda.Event()
+            slot.done_ev.record(self.s_decide)
+
+    def finish(self):
+        """Issue what is still pending and make the caller's current stream wait for every tick."""
+        if self.cuda:
+            self._issue_pending_decide()
+            cur = torch.cuda.current_stream(self.dev)
+            cur.wait_stream(self.s_decide)
+            cur.wait_stream(self.s_route)
+
+    def step(self, d_req, d_res):
+        n_recv = self.submit(d_req, d_res)
+        self.finish()
         return n_recv
