@@ -178,6 +178,8 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # the all-to-alls are pairwise sends over NVLink/NVSwitch: give each peer pair more channels
+        os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "8")
         dist.init_process_group("nccl", device_id=dev)
 
     W, K = max(args.warmup, 3), args.steps
