@@ -37,6 +37,10 @@ enum {
     GCRA_STORE_MANUAL = 3         /* never sweeps on its own; call gcra_sweep()                                     */
 };
 
+/* tests only: size the table at 1x capacity and fill it to 15/16 before growing, so that the
+ * second-choice buckets, the stash and table growth are exercised by small traces */
+#define GCRA_FLAG_TIGHT_TABLE 1u
+
 typedef struct gcra_engine gcra_engine;
 
 typedef struct {
@@ -46,7 +50,7 @@ typedef struct {
     uint64_t p0, p1, p2;  /* policy parameters, 0 = the reference's library default */
     int64_t created_ns;   /* stands in for SystemTime::now() in the constructors (adaptive_cleanup.rs:94) */
     uint32_t max_batch;   /* largest number of requests one kernel pass carries (0 -> 1<<20) */
-    uint32_t flags;       /* reserved, 0 */
+    uint32_t flags;       /* GCRA_FLAG_* */
 } gcra_config;
 
 /* One call of RateLimiter::rate_limit(key, max_burst, count_per_period, period, quantity, now)

@@ -173,3 +173,34 @@ def test_sweep_removes_exactly_the_expired():
         assert removed == sto.force_sweep(traces.T0 + dt)
         assert st.len() == sto.len()
     assert st.len() == 0 or st.len() < n_keys
+
+
+@pytest.mark.parametrize("batch", [64, 4096])
+def test_tight_table_stash_and_growth(batch):
+    """GCRA_FLAG_TIGHT_TABLE: a 64-slot table filled to 15/16 and grown repeatedly while 20 000 keys
+    arrive -- second-choice buckets, stash probing, tombstones after sweeps and rehash all on the path."""
+    n_keys = 20_000
+    rng = np.random.default_rng(5)
+    n = 120_000
+    req = np.zeros(n, traces.REQ_DTYPE)
+    # keys arrive progressively so the table grows many times while old keys stay hot
+    req["key"] = (rng.integers(0, n_keys, n) * np.linspace(0.01, 1.0, n)).astype(np.uint64)
+    traces.fill_policy(req, (req["key"] % np.uint64(8)).astype(np.int64))
+    req["quantity"] = rng.choice([0, 1, 1, 1, 2, 5], n)
+    req["now_ns"] = traces.T0 + np.cumsum(rng.choice([0, 1000, 2_000_000, 700_000_000], n))
+    st_o = oracle.OracleStore(oracle.PERIODIC, capacity=16, created_ns=traces.T0, p0=10**9)
+    res_o = st_o.replay(req)
+    st_e = tc.ManualStore(capacity=16, created_ns=traces.T0, max_batch=4096, flags=1)
+    lim = tc.RateLimiter(st_e)
+    ereq = engine_requests(req)
+    res_e = np.empty(n, tc.RES_DTYPE)
+    swept = 0
+    for a in range(0, n, batch):
+        lim.rate_limit_batch(ereq[a:a + batch], out=res_e[a:a + batch])
+        if (a // batch) % 97 == 96:      # sweeps leave holes and stash tombstones behind
+            swept += st_e.sweep(int(req["now_ns"][min(a + batch, n) - 1]))
+    assert first_mismatch(res_o, res_e, req) is None, first_mismatch(res_o, res_e, req)
+    s = st_e.stats()
+    assert s["grows"] >= 3 and swept > 0
+    assert s["stash_entries"] > 0                 # keys really live in the stash
+    assert s["table_slots"] < 4 * n_keys          # stayed tight: load well above the production 0.5

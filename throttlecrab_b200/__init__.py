@@ -103,12 +103,12 @@ class _GpuStore:
     """A GPU-resident key -> (tat, expiry) table standing in for one reference store."""
     KIND = _native.STORE_ADAPTIVE
 
-    def __init__(self, capacity=1000, device=0, created_ns=None, p0=0, p1=0, p2=0, max_batch=0):
+    def __init__(self, capacity=1000, device=0, created_ns=None, p0=0, p1=0, p2=0, max_batch=0, flags=0):
         import time
         L = _native.lib()
         cfg = _native.Config(capacity=capacity, device=device, store_kind=self.KIND, p0=p0, p1=p1,
                              p2=p2, created_ns=time.time_ns() if created_ns is None else created_ns,
-                             max_batch=max_batch, flags=0)
+                             max_batch=max_batch, flags=flags)
         h = C.c_void_p()
         if L.gcra_create(C.byref(cfg), C.byref(h)) != OK or not h:
             raise RuntimeError("gcra_create failed: the CUDA engine is unavailable "

@@ -51,6 +51,7 @@ struct gcra_engine {
     Table tab{};
     uint32_t total_lines = 0;
     uint64_t capacity = 0;
+    bool tight = false;              // GCRA_FLAG_TIGHT_TABLE: tests only, exercises stash + growth
     // scratch for one batch
     uint32_t max_batch = 0;
     Req *drec = nullptr;
@@ -94,18 +95,18 @@ static uint32_t ceil_log2(uint64_t x) {
     return b;
 }
 
-static void table_geometry(uint64_t capacity, uint32_t &total_lines, uint32_t &nb_main, uint32_t &stash_slots) {
+static void table_geometry(uint64_t capacity, bool tight, uint32_t &total_lines, uint32_t &nb_main, uint32_t &stash_slots) {
     // first-fit two-choice buckets of 4 stay below ~0.4 % stash traffic up to load 0.5
-    uint64_t slots = 1ULL << ceil_log2(std::max<uint64_t>(capacity * 2, 256));
+    uint64_t slots = 1ULL << ceil_log2(std::max<uint64_t>(tight ? capacity : capacity * 2, tight ? 64 : 256));
     total_lines = (uint32_t)(slots / 4);
-    uint32_t ns = std::max<uint32_t>(total_lines / 64, 8);
+    uint32_t ns = std::max<uint32_t>(tight ? total_lines / 4 : total_lines / 64, 8);
     nb_main = total_lines - ns;
     stash_slots = (ns - 1) * 4;   // the last line is reserved (null slot)
 }
 
 static int alloc_table(gcra_engine *h, uint64_t capacity, Table &t, uint32_t &total_lines, u64 *counters) {
     uint32_t nb, ss;
-    table_geometry(capacity, total_lines, nb, ss);
+    table_geometry(capacity, h->tight, total_lines, nb, ss);
     const size_t slots = (size_t)total_lines * 4;
     CK(cudaMalloc(&t.keys, slots * sizeof(u64)));
     CK(cudaMalloc(&t.state, slots * sizeof(TatOff)));
@@ -122,7 +123,17 @@ static int alloc_table(gcra_engine *h, uint64_t capacity, Table &t, uint32_t &to
     return GCRA_OK;
 }
 
-static uint64_t load_limit(const gcra_engine *h) { return (uint64_t)h->tab.nb_main * 4 / 2; }
+static uint64_t load_limit(const gcra_engine *h) {
+    uint64_t main_slots = (uint64_t)h->tab.nb_main * 4;
+    return h->tight ? main_slots * 13 / 16 : main_slots / 2;
+}
+
+static uint64_t load_limit_for(uint64_t capacity, bool tight) {
+    uint32_t tl, nb, ss;
+    table_geometry(capacity, tight, tl, nb, ss);
+    uint64_t main_slots = (uint64_t)nb * 4;
+    return tight ? main_slots * 13 / 16 : main_slots / 2;
+}
 
 static int refresh_counters(gcra_engine *h, bool wait) {
     CK(cudaMemcpyAsync(h->h_counters, h->tab.counters, C_COUNT * sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
@@ -161,7 +172,7 @@ static int do_sweep(gcra_engine *h, int64_t now_ns, uint64_t *removed) {
 static int grow(gcra_engine *h, uint64_t need) {
     CK(cudaStreamSynchronize(h->stream));
     uint64_t newcap = std::max<uint64_t>(h->capacity * 2, 256);
-    while (newcap < need) newcap *= 2;
+    while (load_limit_for(newcap, h->tight) < need) newcap *= 2;
     Table nt{};
     uint32_t nl = 0;
     u64 *ncounters = nullptr;
@@ -376,6 +387,7 @@ int32_t gcra_create(const gcra_config *cfg, gcra_engine **out) {
     cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking);
     h->capacity = cfg->capacity ? cfg->capacity : 1000;      // DEFAULT_CAPACITY adaptive_cleanup.rs:10
     h->max_batch = cfg->max_batch ? cfg->max_batch : (1u << 20);
+    h->tight = (cfg->flags & GCRA_FLAG_TIGHT_TABLE) != 0;
     u64 *counters = nullptr;
     if ((e = cudaMalloc(&counters, C_COUNT * sizeof(u64))) != cudaSuccess) return fail("counters", e);
     cudaMemsetAsync(counters, 0, C_COUNT * sizeof(u64), h->stream);
