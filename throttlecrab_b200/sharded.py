@@ -59,6 +59,7 @@ class _Slot:
         self.src_index = torch.empty(max_rows, dtype=torch.int32, device=device)
         self.counts = torch.zeros(16, dtype=torch.int32, device=device)
         self.recv_counts = torch.zeros(16, dtype=torch.int32, device=device)
+        self.both_host = torch.empty(32, dtype=torch.int32, pin_memory=(device.type == "cuda"))
         self.routed_ev = None      # request all-to-all finished
         self.decided_ev = None     # engine kernels finished
         self.done_ev = None        # results un-permuted into the caller's buffer
@@ -73,6 +74,7 @@ class ShardedLimiter:
         self.cuda = device.type == "cuda"
         self.slots = [_Slot(self.max_rows, device) for _ in range(DEPTH if self.cuda else 1)]
         self.n_submitted = 0
+        self.pending = None
         self.last_recv_rows = 0
         # one communicator per stage (NCCL executes the collectives of ONE communicator in issue order)
         self.pg_counts = dist.new_group()
@@ -83,19 +85,33 @@ class ShardedLimiter:
             self.s_decide = torch.cuda.Stream(device)
             self.s_return = torch.cuda.Stream(device)
 
-    # ------------------------------------------------------------------ the two halves of a tick
-    def _route(self, slot, d_req, n, stream):
-        W, dist = self.world, self.dist
+    # ------------------------------------------------------------------ the stages of a tick
+    def _route_a(self, slot, d_req, n, stream):
+        """partition + count exchange (asynchronous)"""
+        W = self.world
         self.ops.partition(n, d_req, W, slot.routed, slot.src_index, slot.counts, stream)
-        dist.all_to_all_single(slot.recv_counts[:W], slot.counts[:W], group=self.pg_counts)
-        both = torch.cat([slot.counts[:W], slot.recv_counts[:W]]).tolist()   # host sync of the ROUTE stream only
+        self.dist.all_to_all_single(slot.recv_counts[:W], slot.counts[:W], group=self.pg_counts)
+        slot.both = torch.cat([slot.counts[:W], slot.recv_counts[:W]])
+        if self.cuda:
+            slot.both_host[:2 * W].copy_(slot.both, non_blocking=True)
+            slot.counts_ev = torch.cuda.Event()
+            slot.counts_ev.record()
+
+    def _route_b(self, slot, n):
+        """read the counts on the host (the only host sync of a tick), then the request all-to-all"""
+        W = self.world
+        if self.cuda:
+            slot.counts_ev.synchronize()
+            both = slot.both_host[:2 * W].tolist()
+        else:
+            both = slot.both.tolist()
         send_l, recv_l = both[:W], both[W:]
         n_recv = sum(recv_l)
         if n_recv > self.max_rows:
             raise RuntimeError("shard received %d rows > max_batch %d" % (n_recv, self.max_rows))
-        dist.all_to_all_single(slot.recv_req[:n_recv * REQ_B], slot.routed[:n * REQ_B],
-                               output_split_sizes=[c * REQ_B for c in recv_l],
-                               input_split_sizes=[c * REQ_B for c in send_l], group=self.pg_req)
+        self.dist.all_to_all_single(slot.recv_req[:n_recv * REQ_B], slot.routed[:n * REQ_B],
+                                    output_split_sizes=[c * REQ_B for c in recv_l],
+                                    input_split_sizes=[c * REQ_B for c in send_l], group=self.pg_req)
         return send_l, recv_l, n_recv
 
     def _decide(self, slot, n_recv, stream):
@@ -107,28 +123,11 @@ class ShardedLimiter:
                                     input_split_sizes=[c * RES_B for c in recv_l], group=self.pg_res)
         self.ops.unpermute(n, slot.back_res, slot.src_index, d_res, stream)
 
-    # ------------------------------------------------------------------ public
-    def submit(self, d_req, d_res):
-        """Enqueue one tick.  d_req: uint8 tensor of n*48 bytes (gcra_request rows), ready on the
-        caller's current stream; d_res: uint8 tensor of n*32 bytes, valid after finish()."""
-        n = d_req.numel() // REQ_B
-        slot = self.slots[self.n_submitted % len(self.slots)]
-        self.n_submitted += 1
-        if not self.cuda:
-            send_l, recv_l, n_recv = self._route(slot, d_req, n, None)
-            self._decide(slot, n_recv, None)
-            self._return(slot, d_res, n, send_l, recv_l, n_recv, None)
-            self.last_recv_rows = n_recv
-            return n_recv
-        ready = torch.cuda.Event()
-        ready.record(torch.cuda.current_stream(self.dev))
-        with torch.cuda.stream(self.s_route):
-            self.s_route.wait_event(ready)
-            if slot.done_ev is not None:
-                self.s_route.wait_event(slot.done_ev)            # the slot's buffers are free again
-            send_l, recv_l, n_recv = self._route(slot, d_req, n, self.s_route.cuda_stream)
-            slot.routed_ev = torch.cuda.Event()
-            slot.routed_ev.record(self.s_route)
+    def _issue_decide_return(self):
+        if self.pending is None:
+            return
+        slot, d_res, n, send_l, recv_l, n_recv = self.pending
+        self.pending = None
         with torch.cuda.stream(self.s_decide):
             self.s_decide.wait_event(slot.routed_ev)
             self._decide(slot, n_recv, self.s_decide.cuda_stream)
@@ -139,12 +138,43 @@ class ShardedLimiter:
             self._return(slot, d_res, n, send_l, recv_l, n_recv, self.s_return.cuda_stream)
             slot.done_ev = torch.cuda.Event()
             slot.done_ev.record(self.s_return)
+
+    # ------------------------------------------------------------------ public
+    def submit(self, d_req, d_res):
+        """Enqueue one tick.  d_req: uint8 tensor of n*48 bytes (gcra_request rows), ready on the
+        caller's current stream; d_res: uint8 tensor of n*32 bytes, valid after finish()."""
+        n = d_req.numel() // REQ_B
+        slot = self.slots[self.n_submitted % len(self.slots)]
+        self.n_submitted += 1
+        if not self.cuda:
+            self._route_a(slot, d_req, n, None)
+            send_l, recv_l, n_recv = self._route_b(slot, n)
+            self._decide(slot, n_recv, None)
+            self._return(slot, d_res, n, send_l, recv_l, n_recv, None)
+            self.last_recv_rows = n_recv
+            return n_recv
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(self.s_route):
+            self.s_route.wait_event(ready)
+            if slot.done_ev is not None:
+                self.s_route.wait_event(slot.done_ev)            # the slot's buffers are free again
+            self._route_a(slot, d_req, n, self.s_route.cuda_stream)
+        # while the partition + count exchange of THIS tick run, enqueue the previous tick's engine
+        # kernels and result return: the count read-back below then finds its data ready
+        self._issue_decide_return()
+        with torch.cuda.stream(self.s_route):
+            send_l, recv_l, n_recv = self._route_b(slot, n)
+            slot.routed_ev = torch.cuda.Event()
+            slot.routed_ev.record(self.s_route)
+        self.pending = (slot, d_res, n, send_l, recv_l, n_recv)
         self.last_recv_rows = n_recv
         return n_recv
 
     def finish(self):
-        """Make the caller's current stream wait for every submitted tick."""
+        """Issue what is still pending and make the caller's current stream wait for every tick."""
         if self.cuda:
+            self._issue_decide_return()
             cur = torch.cuda.current_stream(self.dev)
             for st in (self.s_route, self.s_decide, self.s_return):
                 cur.wait_stream(st)
