@@ -195,9 +195,10 @@ def test_tight_table_stash_and_growth(batch):
     ereq = engine_requests(req)
     res_e = np.empty(n, tc.RES_DTYPE)
     swept = 0
+    every = max(1, 6000 // batch)
     for a in range(0, n, batch):
         lim.rate_limit_batch(ereq[a:a + batch], out=res_e[a:a + batch])
-        if (a // batch) % 97 == 96:      # sweeps leave holes and stash tombstones behind
+        if (a // batch) % every == every - 1:      # sweeps leave holes and stash tombstones behind
             swept += st_e.sweep(int(req["now_ns"][min(a + batch, n) - 1]))
     assert first_mismatch(res_o, res_e, req) is None, first_mismatch(res_o, res_e, req)
     s = st_e.stats()

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -382,6 +383,7 @@ int32_t gcra_create(const gcra_config *cfg, gcra_engine **out) {
     if (cfg->device < 0 || cfg->device >= ndev) return fail("bad device ordinal", cudaErrorInvalidDevice);
     h->device = cfg->device;
     if ((e = cudaSetDevice(h->device)) != cudaSuccess) return fail("cudaSetDevice", e);
+    if (const char *g = getenv("GCRA_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
     cudaStreamCreateWithFlags(&h->in_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking);

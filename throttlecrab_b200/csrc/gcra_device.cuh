@@ -149,8 +149,20 @@ __device__ __forceinline__ Outputs outputs_of(const Decision &d, const Req &r) {
     Outputs o;
     i64 cur = d.allowed ? d.new_tat : d.tat;
     i64 room = sat_sub(wrap_add(r.now, r.dvt), cur);
+    // remaining = max(room / ei, 0) for ei > 0 (truncating).  room <= 0 gives 0.  Both operands below 2^53
+    // (always, away from saturation corners): one IEEE double division, exact after a +-1 correction;
+    // otherwise the 64-bit integer division.
     i64 rem = 0;
-    if (r.ei > 0) { rem = room / r.ei; if (rem < 0) rem = 0; }
+    if (r.ei > 0 && room > 0) {
+        if ((u64)(room | r.ei) < (1ULL << 53)) {
+            i64 q = (i64)__ddiv_rn(__ll2double_rn(room), __ll2double_rn(r.ei));
+            i64 rr = room - q * r.ei;
+            if (rr < 0) q--; else if (rr >= r.ei) q++;
+            rem = q;
+        } else {
+            rem = room / r.ei;
+        }
+    }
     o.remaining = rem;
     i64 reset = sat_add(sat_sub(cur, r.now), r.dvt);
     o.reset_after = reset < 0 ? 0 : reset;

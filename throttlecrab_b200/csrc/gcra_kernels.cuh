@@ -364,7 +364,7 @@ __device__ __forceinline__ void store_state(const Table &t, u32 slot, const RunS
     if (created) t.ei[slot] = s.ei;
 }
 
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(TILE_THREADS, 4)
 decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ drec, u32 n,
               gcra_result *__restrict__ out, LongRun *__restrict__ long_runs, LongRun *__restrict__ giant_runs,
               u32 *__restrict__ long_count) {
@@ -506,12 +506,10 @@ decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ d
     }
 
     // warp-aggregated counters
-    for (int o = 16; o > 0; o >>= 1) {
-        n_allowed += __shfl_xor_sync(0xffffffffu, n_allowed, o);
-        n_denied += __shfl_xor_sync(0xffffffffu, n_denied, o);
-        real_inc += __shfl_xor_sync(0xffffffffu, real_inc, o);
-        exp_hits += __shfl_xor_sync(0xffffffffu, exp_hits, o);
-    }
+    n_allowed = __reduce_add_sync(0xffffffffu, n_allowed);
+    n_denied = __reduce_add_sync(0xffffffffu, n_denied);
+    real_inc = __reduce_add_sync(0xffffffffu, real_inc);
+    exp_hits = __reduce_add_sync(0xffffffffu, exp_hits);
     if (lane == 0) {
         if (n_allowed) atomicAdd(&t.counters[C_ALLOWED], (u64)n_allowed);
         if (n_denied) atomicAdd(&t.counters[C_DENIED], (u64)n_denied);
@@ -759,12 +757,10 @@ decide_runs_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restric
         __syncthreads();
     }
     if (CTAS > 1) cg::this_cluster().sync();   // nobody leaves while its shared memory may be accessed remotely
-    for (int o = 16; o > 0; o >>= 1) {
-        n_allowed += __shfl_xor_sync(0xffffffffu, n_allowed, o);
-        n_denied += __shfl_xor_sync(0xffffffffu, n_denied, o);
-        real_inc += __shfl_xor_sync(0xffffffffu, real_inc, o);
-        exp_hits += __shfl_xor_sync(0xffffffffu, exp_hits, o);
-    }
+    n_allowed = __reduce_add_sync(0xffffffffu, n_allowed);
+    n_denied = __reduce_add_sync(0xffffffffu, n_denied);
+    real_inc = __reduce_add_sync(0xffffffffu, real_inc);
+    exp_hits = __reduce_add_sync(0xffffffffu, exp_hits);
     if (lane == 0) {
         if (n_allowed) atomicAdd(&t.counters[C_ALLOWED], (u64)n_allowed);
         if (n_denied) atomicAdd(&t.counters[C_DENIED], (u64)n_denied);

@@ -75,6 +75,7 @@ class ShardedLimiter:
         self.slots = [_Slot(self.max_rows, device) for _ in range(DEPTH if self.cuda else 1)]
         self.n_submitted = 0
         self.pending = None
+        self.returned = []
         self.last_recv_rows = 0
         # one communicator per stage (NCCL executes the collectives of ONE communicator in issue order)
         self.pg_counts = dist.new_group()
@@ -138,6 +139,13 @@ class ShardedLimiter:
             self._return(slot, d_res, n, send_l, recv_l, n_recv, self.s_return.cuda_stream)
             slot.done_ev = torch.cuda.Event()
             slot.done_ev.record(self.s_return)
+        self.returned.append(slot.done_ev)
+
+    def pop_returned(self):
+        """Events of the ticks whose results are (or will be) in their d_res buffers, oldest first;
+        lets a caller chain per-tick device->host copies without waiting for finish()."""
+        out, self.returned = self.returned, []
+        return out
 
     # ------------------------------------------------------------------ public
     def submit(self, d_req, d_res):
