@@ -74,6 +74,14 @@ struct gcra_engine {
     bool ev_valid = false;
     uint64_t launches = 0;
     uint64_t occupied_ub = 0;        // host-side upper bound of claimed slots
+    // asynchronous occupancy snapshots: counters copied after every batch, read when their event is done
+    static const int N_SNAP = 8;
+    u64 *h_snap = nullptr;           // pinned [N_SNAP][C_COUNT]
+    cudaEvent_t ev_snap[N_SNAP] = {};
+    uint64_t snap_rows_after[N_SNAP] = {};   // rows launched up to and including the snapshot's batch
+    bool snap_used[N_SNAP] = {};
+    uint32_t snap_next = 0;
+    uint64_t rows_launched = 0;
     // store policy (mirrors the reference stores' fields)
     int kind = GCRA_STORE_ADAPTIVE;
     __int128 next_cleanup = 0, cleanup_interval = 0;
@@ -145,6 +153,7 @@ static int refresh_counters(gcra_engine *h, bool wait) {
 
 static int do_sweep(gcra_engine *h, int64_t now_ns, uint64_t *removed) {
     CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());   // the sweep is exclusive: batches may be in flight on caller streams
     RC(refresh_counters(h, true));
     uint64_t before = h->h_counters[C_SWEPT];
     uint32_t grid = (uint32_t)std::min<uint64_t>(((uint64_t)h->total_lines * 4 + TILE_THREADS * SWEEP_UNROLL - 1) / (TILE_THREADS * SWEEP_UNROLL), 148 * 16);
@@ -164,6 +173,7 @@ static int do_sweep(gcra_engine *h, int64_t now_ns, uint64_t *removed) {
         CK(cudaGetLastError());
     }
     h->occupied_ub = h->h_counters[C_OCCUPIED];
+    for (int i = 0; i < gcra_engine::N_SNAP; i++) h->snap_used[i] = false;
     h->n_sweeps++;
     if (removed) *removed = h->h_counters[C_SWEPT] - before;
     return GCRA_OK;
@@ -204,13 +214,28 @@ static int grow(gcra_engine *h, uint64_t need) {
     h->total_lines = nl;
     h->capacity = newcap;
     h->occupied_ub = keep[C_OCCUPIED];
+    for (int i = 0; i < gcra_engine::N_SNAP; i++) h->snap_used[i] = false;
     h->n_grows++;
     return GCRA_OK;
 }
 
 static int ensure_room(gcra_engine *h, uint64_t n) {
     if (h->occupied_ub + n <= load_limit(h)) { h->occupied_ub += n; return GCRA_OK; }
+    // the bound is stale (it assumes every request claimed a slot): tighten it from the newest
+    // counter snapshot that has already arrived, without stalling the stream
+    for (int back = 1; back <= gcra_engine::N_SNAP; back++) {
+        int k = (int)((h->snap_next + gcra_engine::N_SNAP - back) % gcra_engine::N_SNAP);
+        if (!h->snap_used[k]) break;
+        if (cudaEventQuery(h->ev_snap[k]) != cudaSuccess) continue;
+        uint64_t ub = h->h_snap[(size_t)k * C_COUNT + C_OCCUPIED] + (h->rows_launched - h->snap_rows_after[k]);
+        if (ub < h->occupied_ub) h->occupied_ub = ub;
+        break;
+    }
+    if (h->occupied_ub + n <= load_limit(h)) { h->occupied_ub += n; return GCRA_OK; }
     int rc = refresh_counters(h, true);
+    if (rc) return rc;
+    CK(cudaDeviceSynchronize());   // batches may be in flight on caller streams
+    rc = refresh_counters(h, true);
     if (rc) return rc;
     h->occupied_ub = h->h_counters[C_OCCUPIED];
     if (h->occupied_ub + n > load_limit(h)) {
@@ -218,6 +243,17 @@ static int ensure_room(gcra_engine *h, uint64_t n) {
         if (rc) return rc;
     }
     h->occupied_ub += n;
+    return GCRA_OK;
+}
+
+static int snapshot_async(gcra_engine *h, uint64_t n, cudaStream_t st) {
+    h->rows_launched += n;
+    int k = (int)h->snap_next;
+    h->snap_next = (h->snap_next + 1) % gcra_engine::N_SNAP;
+    CK(cudaMemcpyAsync(h->h_snap + (size_t)k * C_COUNT, h->tab.counters, C_COUNT * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(h->ev_snap[k], st));
+    h->snap_rows_after[k] = h->rows_launched;
+    h->snap_used[k] = true;
     return GCRA_OK;
 }
 
@@ -360,7 +396,7 @@ static int launch_batch(gcra_engine *h, uint32_t n, const void *d_req, bool comp
     h->launches++;
     if (timed) { CK(cudaEventRecord(h->ev[3], st)); h->ev_valid = true; }
     CK(cudaGetLastError());
-    return GCRA_OK;
+    return snapshot_async(h, n, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -413,10 +449,12 @@ int32_t gcra_create(const gcra_config *cfg, gcra_engine **out) {
               cudaMalloc(&h->giant_runs, (mb / GIANT_RUN_MIN + 1) * sizeof(LongRun)) == cudaSuccess &&
               cudaMalloc(&h->long_count, 2 * sizeof(u32)) == cudaSuccess &&
               cudaMallocHost(&h->h_op, 2 * sizeof(StoreOpResult)) == cudaSuccess &&
-              cudaMallocHost(&h->h_counters, C_COUNT * sizeof(u64)) == cudaSuccess;
+              cudaMallocHost(&h->h_counters, C_COUNT * sizeof(u64)) == cudaSuccess &&
+              cudaMallocHost(&h->h_snap, (size_t)gcra_engine::N_SNAP * C_COUNT * sizeof(u64)) == cudaSuccess;
     if (!ok) return fail("scratch allocation", cudaGetLastError());
     memset(h->h_counters, 0, C_COUNT * sizeof(u64));
     cudaEventCreateWithFlags(&h->ev_counters, cudaEventDisableTiming);
+    for (int i = 0; i < gcra_engine::N_SNAP; i++) cudaEventCreateWithFlags(&h->ev_snap[i], cudaEventDisableTiming);
     for (int i = 0; i < 4; i++) cudaEventCreate(&h->ev[i]);
     cudaEventCreate(&h->ev_sweep[0]);
     cudaEventCreate(&h->ev_sweep[1]);
@@ -451,7 +489,8 @@ void gcra_destroy(gcra_engine *h) {
     cudaFree(h->tab.keys); cudaFree(h->tab.state); cudaFree(h->tab.ei); cudaFree(h->tab.counters);
     cudaFree(h->drec); cudaFree(h->keys_a); cudaFree(h->keys_b); cudaFree(h->hist); cudaFree(h->tot);
     cudaFree(h->d_req); cudaFree(h->d_res); cudaFree(h->route_counts); cudaFree(h->long_runs); cudaFree(h->giant_runs); cudaFree(h->long_count); cudaFree(h->d_pol); cudaFree(h->d_op);
-    cudaFreeHost(h->h_op); cudaFreeHost(h->h_counters);
+    cudaFreeHost(h->h_op); cudaFreeHost(h->h_counters); cudaFreeHost(h->h_snap);
+    for (int i = 0; i < gcra_engine::N_SNAP; i++) cudaEventDestroy(h->ev_snap[i]);
     cudaEventDestroy(h->ev_counters);
     for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]);
     cudaEventDestroy(h->ev_sweep[0]); cudaEventDestroy(h->ev_sweep[1]);
