@@ -48,7 +48,8 @@ struct RingSlot {
 
 struct gcra_engine {
     int device = 0;
-    cudaStream_t stream = nullptr, in_stream = nullptr, out_stream = nullptr;
+    cudaStream_t stream = nullptr, in_stream = nullptr, out_stream = nullptr, aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     Table tab{};
     uint32_t total_lines = 0;
     uint64_t capacity = 0;
@@ -384,12 +385,17 @@ static int launch_batch(gcra_engine *h, uint32_t n, const void *d_req, bool comp
     decide_kernel<<<(warps + TILE_THREADS / 32 - 1) / (TILE_THREADS / 32), TILE_THREADS, 0, st>>>(
         h->tab, src, h->drec, n, d_res, h->long_runs, h->giant_runs, h->long_count);
     if (n >= GIANT_RUN_MIN) {
+        // the two hot-run kernels work on disjoint runs: the one-CTA-per-run kernel goes to a side
+        // stream and overlaps the cluster kernel (fork/join with events)
+        CK(cudaEventRecord(h->ev_fork, st));
+        CK(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
+        decide_runs_kernel<1><<<148, LONG_THREADS, 0, h->aux_stream>>>(h->tab, src, h->drec, d_res, h->long_runs, h->long_count);
+        CK(cudaEventRecord(h->ev_join, h->aux_stream));
         // hottest keys: one 8-CTA cluster per run, persistent over the work list
         RC(launch_giant(h, src, d_res, st));
-        h->launches++;
-    }
-    if (n >= LONG_RUN_MIN) {
-        // hot keys (runs of >= LONG_RUN_MIN requests): one CTA each, persistent over the work list
+        CK(cudaStreamWaitEvent(st, h->ev_join, 0));
+        h->launches += 2;
+    } else if (n >= LONG_RUN_MIN) {
         decide_runs_kernel<1><<<148, LONG_THREADS, 0, st>>>(h->tab, src, h->drec, d_res, h->long_runs, h->long_count);
         h->launches++;
     }
@@ -423,6 +429,9 @@ int32_t gcra_create(const gcra_config *cfg, gcra_engine **out) {
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
     cudaStreamCreateWithFlags(&h->in_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
     h->capacity = cfg->capacity ? cfg->capacity : 1000;      // DEFAULT_CAPACITY adaptive_cleanup.rs:10
     h->max_batch = cfg->max_batch ? cfg->max_batch : (1u << 20);
     h->tight = (cfg->flags & GCRA_FLAG_TIGHT_TABLE) != 0;
@@ -494,7 +503,8 @@ void gcra_destroy(gcra_engine *h) {
     cudaEventDestroy(h->ev_counters);
     for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]);
     cudaEventDestroy(h->ev_sweep[0]); cudaEventDestroy(h->ev_sweep[1]);
-    cudaStreamDestroy(h->stream); cudaStreamDestroy(h->in_stream); cudaStreamDestroy(h->out_stream);
+    cudaStreamDestroy(h->stream); cudaStreamDestroy(h->in_stream); cudaStreamDestroy(h->out_stream); cudaStreamDestroy(h->aux_stream);
+    cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join);
     delete h;
 }
 

@@ -275,9 +275,7 @@ sort_scatter_kernel(const u64 *__restrict__ in, u64 *__restrict__ outk, u32 n, u
 // that lane's new state is shuffled to the lanes behind it and only they re-evaluate.  The loop
 // runs (state changes in the busiest run of the chunk + 1) times, and yields exactly the results
 // of applying the requests one after another.
-struct RunState { i64 tat, exp, ei; };
-
-struct LaneOut { Decision d; bool done; };
+struct RunState { i64 tat, exp, ei; };   // ei: informational column only, never part of a decision
 
 __device__ __forceinline__ void run_chunk(u32 lane, bool mine, u32 gmask, const Req &r, RunState &s,
                                           Decision &fin, bool &changed_any, u32 &n_exp_hits) {
@@ -288,12 +286,12 @@ __device__ __forceinline__ void run_chunk(u32 lane, bool mine, u32 gmask, const 
     for (;;) {
         Decision d;
         bool mut = false;
-        RunState so = s;
+        i64 so_tat = s.tat, so_exp = s.exp;
         if (pending) {
             d = decide(s.tat, s.exp, r);
             if (d.allowed) {
-                so.tat = d.new_tat; so.exp = d.new_exp; so.ei = r.ei;
-                mut = (so.tat != s.tat) | (so.exp != s.exp);
+                so_tat = d.new_tat; so_exp = d.new_exp;
+                mut = (so_tat != s.tat) | (so_exp != s.exp);
             }
         }
         const u32 P = __ballot_sync(0xffffffffu, pending);
@@ -301,19 +299,17 @@ __device__ __forceinline__ void run_chunk(u32 lane, bool mine, u32 gmask, const 
         const u32 M = __ballot_sync(0xffffffffu, pending && mut);
         const u32 prior = M & gmask & lt;
         const int src = prior ? (__ffs(prior) - 1) : (int)lane;
-        RunState sn;
-        sn.tat = __shfl_sync(0xffffffffu, so.tat, src);
-        sn.exp = __shfl_sync(0xffffffffu, so.exp, src);
-        sn.ei = __shfl_sync(0xffffffffu, so.ei, src);
+        const i64 sn_tat = __shfl_sync(0xffffffffu, so_tat, src);
+        const i64 sn_exp = __shfl_sync(0xffffffffu, so_exp, src);
         if (pending) {
             if (prior == 0) {
                 fin = d;
                 // a write over an entry that exists but is expired (adaptive_cleanup.rs:233,267)
                 if (d.allowed && !d.live && s.exp >= 0) n_exp_hits++;
-                if (mut) { s = so; mflag = true; }
+                if (mut) { s.tat = so_tat; s.exp = so_exp; mflag = true; }
                 pending = false;
             } else {
-                s = sn;
+                s.tat = sn_tat; s.exp = sn_exp;
             }
         }
     }
@@ -391,7 +387,16 @@ decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ d
     const u32 heads = __ballot_sync(0xffffffffu, head);
     const u32 le = (lane == 31) ? 0xffffffffu : ((2u << lane) - 1);
     const int hl = mine ? (31 - __clz(heads & le)) : (int)lane;
-    const u32 gmask = __match_any_sync(0xffffffffu, mine ? hl : (int)(32 + lane));
+    // lanes of my run: from my head lane up to (not including) the next head, among `mine` lanes
+    u32 gmask = 1u << lane;
+    {
+        const u32 mine_m = __ballot_sync(0xffffffffu, mine);
+        if (mine) {
+            const u32 above = heads & ~((hl == 31) ? 0xffffffffu : ((2u << hl) - 1));   // heads after mine
+            const u32 upto = above ? ((1u << (__ffs(above) - 1)) - 1) : 0xffffffffu;     // lanes below the next head
+            gmask = mine_m & upto & ~((1u << hl) - 1);
+        }
+    }
 
     // does the chunk's last run continue past the chunk?  (uniform)
     const u32 slot31 = __shfl_sync(0xffffffffu, slot, 31);
@@ -423,7 +428,6 @@ decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ d
     if (head && mine) load_state(t, slot, s);
     s.tat = __shfl_sync(0xffffffffu, s.tat, hl);
     s.exp = __shfl_sync(0xffffffffu, s.exp, hl);
-    s.ei = __shfl_sync(0xffffffffu, s.ei, hl);
     const bool was_phantom = s.exp == EXP_PHANTOM;   // same for every lane of the run
 
     Decision fin;
@@ -459,7 +463,7 @@ decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ d
         RunState cs;
         cs.tat = __shfl_sync(0xffffffffu, s.tat, 31);
         cs.exp = __shfl_sync(0xffffffffu, s.exp, 31);
-        cs.ei = __shfl_sync(0xffffffffu, s.ei, 31);
+        cs.ei = __shfl_sync(0xffffffffu, s.ei, 31);   // (set below: ei of the run's first request)
         bool c_changed = __shfl_sync(0xffffffffu, run_changed ? 1 : 0, 31) != 0;
         const bool c_phantom = __shfl_sync(0xffffffffu, was_phantom ? 1 : 0, 31) != 0;
         u32 b2 = base + 32;
@@ -494,7 +498,6 @@ decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ d
             const int last = 31 - __clz(rm);
             cs.tat = __shfl_sync(0xffffffffu, s2.tat, last);
             cs.exp = __shfl_sync(0xffffffffu, s2.exp, last);
-            cs.ei = __shfl_sync(0xffffffffu, s2.ei, last);
             if (rm != 0xffffffffu) break;
             b2 = b3; e2 = e3; in_run = in3; r2 = r3;
         }
