@@ -234,7 +234,8 @@ def main():
 
     def step(i):
         if world == 1:
-            lim.rate_limit_batch_device(TICK, d_req[i].data_ptr(), d_res[i].data_ptr(), stream.cuda_stream)
+            # pipelined submission: ingest+order of tick i+1 overlap the decide kernels of tick i
+            lim.submit_device(TICK, d_req[i].data_ptr(), d_res[i].data_ptr(), stream.cuda_stream)
         else:
             sh.submit(d_req[i], d_res[i])       # pipelined: routing of tick i+1 overlaps deciding tick i
 
@@ -243,6 +244,8 @@ def main():
         step(i)
     if world > 1:
         sh.finish()
+    else:
+        lim.join(stream.cuda_stream)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
@@ -261,6 +264,8 @@ def main():
         step_ev[i - W + 1].record(stream)
     if world > 1:
         sh.finish()
+    else:
+        lim.join(stream.cuda_stream)
     ev1.record(stream)
     torch.cuda.synchronize()
     if dist:
@@ -280,8 +285,11 @@ def main():
     n_ok = int((res_np["status"] == 0).sum())
     phases = None
     if world == 1:
-        # re-measure phase split on fresh ticks is not possible without new data; time the LAST
-        # timed tick's phases (events recorded inside the library for every batch)
+        # phase split of ONE tick run serially on the stream (library-side CUDA events); the timed
+        # region above pipelines consecutive ticks, so its per-tick time is below this total
+        extra = torch.empty(TICK * 32, dtype=torch.uint8, device=dev)
+        lim.rate_limit_batch_device(TICK, d_req[W].data_ptr(), extra.data_ptr(), stream.cuda_stream)
+        torch.cuda.synchronize()
         phases = store.last_kernel_ms()
     clocks = sampler.stop() if rank == 0 else None
 
@@ -422,11 +430,11 @@ def main():
     if world == 1:
         t_k1 = total_ms * 1e-3
         ach = alg_bytes / t_k1 / 1e9
-        roof = {"bound": "hbm", "kernel": "K1 = ingest + order + decide (13 launches per tick)",
+        roof = {"bound": "hbm", "kernel": "K1 = ingest + order + decide (13 launches per tick; consecutive ticks pipelined: front half of tick i+1 overlaps the decide kernels of tick i)",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_kind": peak_kind,
                 "traffic": None,
                 "algorithmic_bytes_per_decision": {"allowed": 112, "denied": 96},
-                "last_tick_phase_ms": {"total": phases[0], "ingest": phases[1], "order": phases[2],
+                "serial_tick_phase_ms": {"total": phases[0], "ingest": phases[1], "order": phases[2],
                                        "decide": phases[3]}}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -441,7 +449,7 @@ def main():
                    "l2": "no flush: table %.2f GB and a distinct 80 MB tick per step exceed the 126 MB L2"
                          % (store.stats()["table_slots"] * 32 / 1e9),
                    "allowed_fraction": n_allowed / max(n_ok, 1), "gen_seconds": round(gen_s, 1)},
-        "step_ms": {"min": min(step_ms), "median": float(np.median(step_ms)), "max": max(step_ms)},
+        "host_enqueue_ms_per_step": {"min": min(step_ms), "median": float(np.median(step_ms)), "max": max(step_ms)},
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(line), flush=True)

@@ -140,6 +140,15 @@ int32_t gcra_rate_limit_batch(gcra_engine *h, uint64_t n, const gcra_request *re
 int32_t gcra_rate_limit_batch_device(gcra_engine *h, uint64_t n, const gcra_request *d_req,
                                      gcra_result *d_res, void *stream);
 
+/* pipelined submission: the batch's ingest + ordering run on an engine stream as soon as `ready_stream`
+ * (a cudaStream_t, may be NULL = inputs are ready now) reaches this point, overlapping the decide kernels
+ * of the previously submitted batch; decisions are still applied strictly in submission order.  Results
+ * of all submitted batches are complete once gcra_pipeline_join() has made `stream` wait for them
+ * (stream NULL = block the host). */
+int32_t gcra_rate_limit_batch_device_pipelined(gcra_engine *h, uint64_t n, const gcra_request *d_req,
+                                               gcra_result *d_res, void *ready_stream);
+int32_t gcra_pipeline_join(gcra_engine *h, void *stream);
+
 /* compact requests: register the (max_burst, count, period) table once, then 16-byte requests */
 int32_t gcra_set_policies(gcra_engine *h, uint32_t n, const gcra_policy *policies);
 int32_t gcra_rate_limit_batch16(gcra_engine *h, uint64_t n, const gcra_request16 *req,

@@ -320,6 +320,13 @@ class RateLimiter:
     def rate_limit_batch_device(self, n, d_req_ptr, d_res_ptr, stream=None):
         self.store._check(self._L.gcra_rate_limit_batch_device(self._h, n, d_req_ptr, d_res_ptr, stream))
 
+    def submit_device(self, n, d_req_ptr, d_res_ptr, ready_stream=None):
+        """Pipelined: ingest+order of this batch overlap the decide kernels of the previous one."""
+        self.store._check(self._L.gcra_rate_limit_batch_device_pipelined(self._h, n, d_req_ptr, d_res_ptr, ready_stream))
+
+    def join(self, stream=None):
+        self.store._check(self._L.gcra_pipeline_join(self._h, stream))
+
     def rate_limit_batch16_device(self, n, d_req_ptr, now, d_res_ptr, stream=None):
         self.store._check(self._L.gcra_rate_limit_batch16_device(self._h, n, d_req_ptr, _ns(now), d_res_ptr, stream))
 

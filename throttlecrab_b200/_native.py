@@ -13,7 +13,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 _SRC = os.path.join(_PKG, "csrc")
-SO_PATH = os.path.join(_PKG, "libgcra_b200.so")
+SO_PATH = os.environ.get("GCRA_SO") or os.path.join(_PKG, "libgcra_b200.so")   # GCRA_SO: tuning variants
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC"]
@@ -50,6 +50,8 @@ def sources():
 def build(force=False, verbose=False):
     """nvcc cross-compiles for sm_100a without a GPU; the .so is kept in-tree."""
     srcs = sources()
+    if os.environ.get("GCRA_SO"):
+        return SO_PATH                      # a prebuilt tuning variant
     if not force and os.path.exists(SO_PATH) and all(
             os.path.getmtime(s) <= os.path.getmtime(SO_PATH) for s in srcs):
         return SO_PATH
@@ -76,6 +78,8 @@ SYMBOLS = {
     "gcra_rate_limit": (_i32, [_vp, C.c_char_p, _u64, _i64, _i64, _i64, _i64, _i64, _vp]),
     "gcra_rate_limit_batch": (_i32, [_vp, _u64, _vp, _vp]),
     "gcra_rate_limit_batch_device": (_i32, [_vp, _u64, _vp, _vp, _vp]),
+    "gcra_rate_limit_batch_device_pipelined": (_i32, [_vp, _u64, _vp, _vp, _vp]),
+    "gcra_pipeline_join": (_i32, [_vp, _vp]),
     "gcra_set_policies": (_i32, [_vp, _u32, _vp]),
     "gcra_rate_limit_batch16": (_i32, [_vp, _u64, _vp, _i64, _vp]),
     "gcra_rate_limit_batch16_device": (_i32, [_vp, _u64, _vp, _i64, _vp, _vp]),

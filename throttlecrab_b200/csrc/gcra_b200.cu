@@ -46,24 +46,33 @@ struct RingSlot {
 };
 }  // namespace
 
+// per-batch scratch; two sets so that the front half of one batch can overlap the back half of the previous
+struct Scratch {
+    Req *drec = nullptr;
+    u64 *keys_a = nullptr, *keys_b = nullptr;
+    u32 *hist = nullptr, *tot = nullptr;
+    LongRun *long_runs = nullptr, *giant_runs = nullptr;
+    u32 *long_count = nullptr;
+    cudaEvent_t ev_front = nullptr, ev_back = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    bool back_recorded = false;
+};
+
 struct gcra_engine {
     int device = 0;
     cudaStream_t stream = nullptr, in_stream = nullptr, out_stream = nullptr, aux_stream = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     Table tab{};
     uint32_t total_lines = 0;
     uint64_t capacity = 0;
     bool tight = false;              // GCRA_FLAG_TIGHT_TABLE: tests only, exercises stash + growth
     // scratch for one batch
     uint32_t max_batch = 0;
-    Req *drec = nullptr;
-    u64 *keys_a = nullptr, *keys_b = nullptr;
-    u32 *hist = nullptr, *tot = nullptr;
+    Scratch scr[2];
+    uint32_t scr_next = 0;
+    cudaStream_t front_stream = nullptr, back_stream = nullptr;   // pipelined submission
+    cudaEvent_t ev_ready = nullptr;
     void *d_req = nullptr;
     gcra_result *d_res = nullptr;
     u32 *route_counts = nullptr;
-    LongRun *long_runs = nullptr, *giant_runs = nullptr;
-    u32 *long_count = nullptr;
     PolicyDerived *d_pol = nullptr;
     uint32_t npol = 0;
     StoreOpResult *d_op = nullptr, *h_op = nullptr;
@@ -329,9 +338,9 @@ static int apply_policy(gcra_engine *h, int64_t now_ns) {
 }
 
 // the cluster kernel: cluster dimension given at launch (cudaLaunchKernelEx)
-static int launch_giant(gcra_engine *h, const u64 *src, gcra_result *d_res, cudaStream_t st) {
+static int launch_giant(gcra_engine *h, Scratch &sc, const u64 *src, gcra_result *d_res, cudaStream_t st) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(16 * CLUSTER_CTAS);
+    cfg.gridDim = dim3((128 / CLUSTER_CTAS) * CLUSTER_CTAS);
     cfg.blockDim = dim3(LONG_THREADS);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -341,68 +350,125 @@ static int launch_giant(gcra_engine *h, const u64 *src, gcra_result *d_res, cuda
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CK(cudaLaunchKernelEx(&cfg, decide_runs_kernel<CLUSTER_CTAS>, h->tab, (const u64 *)src, (const Req *)h->drec, d_res,
-                          (const LongRun *)h->giant_runs, (const u32 *)(h->long_count + 1)));
+    if (CLUSTER_CTAS > 8) {
+        static bool once = false;
+        if (!once) { cudaFuncSetAttribute(decide_runs_kernel<CLUSTER_CTAS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); once = true; }
+    }
+    CK(cudaLaunchKernelEx(&cfg, decide_runs_kernel<CLUSTER_CTAS>, h->tab, (const u64 *)src, (const Req *)sc.drec, d_res,
+                          (const LongRun *)sc.giant_runs, (const u32 *)(sc.long_count + 1)));
     return GCRA_OK;
 }
 
-// ---- one batch on a stream -------------------------------------------------------------------
-static int launch_batch(gcra_engine *h, uint32_t n, const void *d_req, bool compact, int64_t now_batch,
-                        gcra_result *d_res, cudaStream_t st, bool timed) {
-    if (n == 0) return GCRA_OK;
-    if (n > h->max_batch) { h->err = "batch larger than max_batch"; return GCRA_INTERNAL; }
-    if (compact && h->npol == 0) { h->err = "no policy table registered"; return GCRA_INTERNAL; }
-    int rc = ensure_room(h, n);
-    if (rc) return rc;
+// front half of a batch: ingest (validate, derive, probe/claim) + stable sort by slot.  Independent of the
+// back half of EARLIER batches: it only claims empty slots (keys array, phantom mark in their state),
+// which no earlier batch's decide kernels touch.
+static int enqueue_front(gcra_engine *h, Scratch &sc, uint32_t n, const void *d_req, bool compact, int64_t now_batch,
+                         gcra_result *d_res, cudaStream_t st, bool timed, u64 **sorted_out) {
     const uint32_t tiles = (n + TILE_THREADS - 1) / TILE_THREADS;
     if (timed) CK(cudaEventRecord(h->ev[0], st));
     if (compact)
         ingest_kernel<true><<<tiles, TILE_THREADS, 0, st>>>(h->tab, d_req, h->d_pol, h->npol, now_batch, n,
-                                                            h->drec, h->keys_a, d_res);
+                                                            sc.drec, sc.keys_a, d_res);
     else
-        ingest_kernel<false><<<tiles, TILE_THREADS, 0, st>>>(h->tab, d_req, nullptr, 0, 0, n, h->drec,
-                                                             h->keys_a, d_res);
+        ingest_kernel<false><<<tiles, TILE_THREADS, 0, st>>>(h->tab, d_req, nullptr, 0, 0, n, sc.drec,
+                                                             sc.keys_a, d_res);
     h->launches++;
     if (timed) CK(cudaEventRecord(h->ev[1], st));
     // stable LSD radix sort over the slot bits
     const uint32_t bits = h->tab.slot_bits;
     const uint32_t passes = (bits + SORT_MAX_BITS - 1) / SORT_MAX_BITS;
     const uint32_t stiles = (n + SORT_TILE - 1) / SORT_TILE;
-    u64 *src = h->keys_a, *dst = h->keys_b;
+    u64 *src = sc.keys_a, *dst = sc.keys_b;
     uint32_t shift = 32;
     for (uint32_t p = 0; p < passes; p++) {
         uint32_t pb = bits / passes + (p < bits % passes ? 1 : 0);
-        sort_hist_kernel<<<stiles, TILE_THREADS, 0, st>>>(src, n, shift, pb, stiles, h->hist);
-        sort_rowscan_kernel<<<1u << pb, TILE_THREADS, 0, st>>>(h->hist, stiles, h->tot);
-        sort_scatter_kernel<<<stiles, TILE_THREADS, 0, st>>>(src, dst, n, shift, pb, stiles, h->hist, h->tot);
+        sort_hist_kernel<<<stiles, TILE_THREADS, 0, st>>>(src, n, shift, pb, stiles, sc.hist);
+        sort_rowscan_kernel<<<1u << pb, TILE_THREADS, 0, st>>>(sc.hist, stiles, sc.tot);
+        sort_scatter_kernel<<<stiles, TILE_THREADS, 0, st>>>(src, dst, n, shift, pb, stiles, sc.hist, sc.tot);
         h->launches += 3;
         std::swap(src, dst);
         shift += pb;
     }
     if (timed) CK(cudaEventRecord(h->ev[2], st));
+    CK(cudaMemsetAsync(sc.long_count, 0, 2 * sizeof(u32), st));
+    *sorted_out = src;
+    return GCRA_OK;
+}
+
+// back half: the compare-and-update kernels; batches' back halves run strictly in submission order
+static int enqueue_back(gcra_engine *h, Scratch &sc, uint32_t n, const u64 *src, gcra_result *d_res, cudaStream_t st,
+                        bool timed) {
     const uint32_t warps = (n + 31) / 32;
-    CK(cudaMemsetAsync(h->long_count, 0, 2 * sizeof(u32), st));
     decide_kernel<<<(warps + TILE_THREADS / 32 - 1) / (TILE_THREADS / 32), TILE_THREADS, 0, st>>>(
-        h->tab, src, h->drec, n, d_res, h->long_runs, h->giant_runs, h->long_count);
+        h->tab, src, sc.drec, n, d_res, sc.long_runs, sc.giant_runs, sc.long_count);
+    h->launches++;
     if (n >= GIANT_RUN_MIN) {
         // the two hot-run kernels work on disjoint runs: the one-CTA-per-run kernel goes to a side
         // stream and overlaps the cluster kernel (fork/join with events)
-        CK(cudaEventRecord(h->ev_fork, st));
-        CK(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
-        decide_runs_kernel<1><<<148, LONG_THREADS, 0, h->aux_stream>>>(h->tab, src, h->drec, d_res, h->long_runs, h->long_count);
-        CK(cudaEventRecord(h->ev_join, h->aux_stream));
-        // hottest keys: one 8-CTA cluster per run, persistent over the work list
-        RC(launch_giant(h, src, d_res, st));
-        CK(cudaStreamWaitEvent(st, h->ev_join, 0));
+        CK(cudaEventRecord(sc.ev_fork, st));
+        CK(cudaStreamWaitEvent(h->aux_stream, sc.ev_fork, 0));
+        decide_runs_kernel<1><<<148, LONG_THREADS, 0, h->aux_stream>>>(h->tab, src, sc.drec, d_res, sc.long_runs, sc.long_count);
+        CK(cudaEventRecord(sc.ev_join, h->aux_stream));
+        RC(launch_giant(h, sc, src, d_res, st));   // hottest keys: one cluster per run
+        CK(cudaStreamWaitEvent(st, sc.ev_join, 0));
         h->launches += 2;
     } else if (n >= LONG_RUN_MIN) {
-        decide_runs_kernel<1><<<148, LONG_THREADS, 0, st>>>(h->tab, src, h->drec, d_res, h->long_runs, h->long_count);
+        decide_runs_kernel<1><<<148, LONG_THREADS, 0, st>>>(h->tab, src, sc.drec, d_res, sc.long_runs, sc.long_count);
         h->launches++;
     }
-    h->launches++;
     if (timed) { CK(cudaEventRecord(h->ev[3], st)); h->ev_valid = true; }
     CK(cudaGetLastError());
+    return GCRA_OK;
+}
+
+static int check_batch(gcra_engine *h, uint32_t n, bool compact) {
+    if (n > h->max_batch) { h->err = "batch larger than max_batch"; return GCRA_INTERNAL; }
+    if (compact && h->npol == 0) { h->err = "no policy table registered"; return GCRA_INTERNAL; }
+    return ensure_room(h, n);
+}
+
+// ---- one batch, everything on the caller's stream ------------------------------------------------
+static int launch_batch(gcra_engine *h, uint32_t n, const void *d_req, bool compact, int64_t now_batch,
+                        gcra_result *d_res, cudaStream_t st, bool timed) {
+    if (n == 0) return GCRA_OK;
+    RC(check_batch(h, n, compact));
+    Scratch &sc = h->scr[h->scr_next];
+    h->scr_next ^= 1;
+    // order after every earlier batch (they may have been submitted pipelined on the engine's streams),
+    // which also frees this scratch set
+    for (auto &o : h->scr) if (o.back_recorded) CK(cudaStreamWaitEvent(st, o.ev_back, 0));
+    u64 *sorted = nullptr;
+    RC(enqueue_front(h, sc, n, d_req, compact, now_batch, d_res, st, timed, &sorted));
+    RC(enqueue_back(h, sc, n, sorted, d_res, st, timed));
+    CK(cudaEventRecord(sc.ev_back, st));
+    sc.back_recorded = true;
     return snapshot_async(h, n, st);
+}
+
+// ---- one batch, pipelined: front half on front_stream, back half on back_stream ------------------
+// The front half of this batch overlaps the back half of the previous one.  `ready` (may be null) is an
+// event after which d_req may be read; `*done` is set to an event after which d_res is complete.
+static int launch_pipelined(gcra_engine *h, uint32_t n, const void *d_req, bool compact, int64_t now_batch,
+                            gcra_result *d_res, cudaEvent_t ready, cudaEvent_t *done) {
+    if (n == 0) { if (done) *done = nullptr; return GCRA_OK; }
+    RC(check_batch(h, n, compact));
+    Scratch &sc = h->scr[h->scr_next];
+    h->scr_next ^= 1;
+    if (ready) CK(cudaStreamWaitEvent(h->front_stream, ready, 0));
+    if (sc.back_recorded) CK(cudaStreamWaitEvent(h->front_stream, sc.ev_back, 0));   // scratch set free again
+    u64 *sorted = nullptr;
+    RC(enqueue_front(h, sc, n, d_req, compact, now_batch, d_res, h->front_stream, false, &sorted));
+    CK(cudaEventRecord(sc.ev_front, h->front_stream));
+    CK(cudaStreamWaitEvent(h->back_stream, sc.ev_front, 0));
+    {   // decisions strictly in submission order, also after a batch submitted on a caller stream
+        Scratch &other = h->scr[h->scr_next];
+        if (other.back_recorded) CK(cudaStreamWaitEvent(h->back_stream, other.ev_back, 0));
+    }
+    RC(enqueue_back(h, sc, n, sorted, d_res, h->back_stream, false));
+    CK(cudaEventRecord(sc.ev_back, h->back_stream));
+    sc.back_recorded = true;
+    if (done) *done = sc.ev_back;
+    return snapshot_async(h, n, h->back_stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -430,8 +496,9 @@ int32_t gcra_create(const gcra_config *cfg, gcra_engine **out) {
     cudaStreamCreateWithFlags(&h->in_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking);
-    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&h->front_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&h->back_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming);
     h->capacity = cfg->capacity ? cfg->capacity : 1000;      // DEFAULT_CAPACITY adaptive_cleanup.rs:10
     h->max_batch = cfg->max_batch ? cfg->max_batch : (1u << 20);
     h->tight = (cfg->flags & GCRA_FLAG_TIGHT_TABLE) != 0;
@@ -445,21 +512,28 @@ int32_t gcra_create(const gcra_config *cfg, gcra_engine **out) {
     }
     const size_t mb = h->max_batch;
     const uint32_t stiles = (uint32_t)((mb + SORT_TILE - 1) / SORT_TILE);
-    bool ok = cudaMalloc(&h->drec, mb * sizeof(Req)) == cudaSuccess &&
-              cudaMalloc(&h->keys_a, mb * sizeof(u64)) == cudaSuccess &&
-              cudaMalloc(&h->keys_b, mb * sizeof(u64)) == cudaSuccess &&
-              cudaMalloc(&h->hist, (size_t)SORT_MAX_DIGITS * stiles * sizeof(u32)) == cudaSuccess &&
-              cudaMalloc(&h->tot, SORT_MAX_DIGITS * sizeof(u32)) == cudaSuccess &&
-              cudaMalloc(&h->d_req, mb * sizeof(gcra_request)) == cudaSuccess &&
+    bool ok = cudaMalloc(&h->d_req, mb * sizeof(gcra_request)) == cudaSuccess &&
               cudaMalloc(&h->d_res, mb * sizeof(gcra_result)) == cudaSuccess &&
               cudaMalloc(&h->route_counts, (size_t)ROUTE_MAX_SHARDS * ((mb + TILE_THREADS - 1) / TILE_THREADS) * sizeof(u32)) == cudaSuccess &&
               cudaMalloc(&h->d_op, 2 * sizeof(StoreOpResult)) == cudaSuccess &&
-              cudaMalloc(&h->long_runs, (mb / LONG_RUN_MIN + 1) * sizeof(LongRun)) == cudaSuccess &&
-              cudaMalloc(&h->giant_runs, (mb / GIANT_RUN_MIN + 1) * sizeof(LongRun)) == cudaSuccess &&
-              cudaMalloc(&h->long_count, 2 * sizeof(u32)) == cudaSuccess &&
               cudaMallocHost(&h->h_op, 2 * sizeof(StoreOpResult)) == cudaSuccess &&
               cudaMallocHost(&h->h_counters, C_COUNT * sizeof(u64)) == cudaSuccess &&
               cudaMallocHost(&h->h_snap, (size_t)gcra_engine::N_SNAP * C_COUNT * sizeof(u64)) == cudaSuccess;
+    for (int k = 0; k < 2 && ok; k++) {
+        Scratch &sc = h->scr[k];
+        ok = cudaMalloc(&sc.drec, mb * sizeof(Req)) == cudaSuccess &&
+             cudaMalloc(&sc.keys_a, mb * sizeof(u64)) == cudaSuccess &&
+             cudaMalloc(&sc.keys_b, mb * sizeof(u64)) == cudaSuccess &&
+             cudaMalloc(&sc.hist, (size_t)SORT_MAX_DIGITS * stiles * sizeof(u32)) == cudaSuccess &&
+             cudaMalloc(&sc.tot, SORT_MAX_DIGITS * sizeof(u32)) == cudaSuccess &&
+             cudaMalloc(&sc.long_runs, (mb / LONG_RUN_MIN + 1) * sizeof(LongRun)) == cudaSuccess &&
+             cudaMalloc(&sc.giant_runs, (mb / GIANT_RUN_MIN + 1) * sizeof(LongRun)) == cudaSuccess &&
+             cudaMalloc(&sc.long_count, 2 * sizeof(u32)) == cudaSuccess &&
+             cudaEventCreateWithFlags(&sc.ev_front, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&sc.ev_back, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&sc.ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&sc.ev_join, cudaEventDisableTiming) == cudaSuccess;
+    }
     if (!ok) return fail("scratch allocation", cudaGetLastError());
     memset(h->h_counters, 0, C_COUNT * sizeof(u64));
     cudaEventCreateWithFlags(&h->ev_counters, cudaEventDisableTiming);
@@ -496,15 +570,19 @@ void gcra_destroy(gcra_engine *h) {
         cudaEventDestroy(s.ev_in); cudaEventDestroy(s.ev_comp); cudaEventDestroy(s.ev_done);
     }
     cudaFree(h->tab.keys); cudaFree(h->tab.state); cudaFree(h->tab.ei); cudaFree(h->tab.counters);
-    cudaFree(h->drec); cudaFree(h->keys_a); cudaFree(h->keys_b); cudaFree(h->hist); cudaFree(h->tot);
-    cudaFree(h->d_req); cudaFree(h->d_res); cudaFree(h->route_counts); cudaFree(h->long_runs); cudaFree(h->giant_runs); cudaFree(h->long_count); cudaFree(h->d_pol); cudaFree(h->d_op);
+    for (auto &sc : h->scr) {
+        cudaFree(sc.drec); cudaFree(sc.keys_a); cudaFree(sc.keys_b); cudaFree(sc.hist); cudaFree(sc.tot);
+        cudaFree(sc.long_runs); cudaFree(sc.giant_runs); cudaFree(sc.long_count);
+        cudaEventDestroy(sc.ev_front); cudaEventDestroy(sc.ev_back); cudaEventDestroy(sc.ev_fork); cudaEventDestroy(sc.ev_join);
+    }
+    cudaFree(h->d_req); cudaFree(h->d_res); cudaFree(h->route_counts); cudaFree(h->d_pol); cudaFree(h->d_op);
     cudaFreeHost(h->h_op); cudaFreeHost(h->h_counters); cudaFreeHost(h->h_snap);
     for (int i = 0; i < gcra_engine::N_SNAP; i++) cudaEventDestroy(h->ev_snap[i]);
     cudaEventDestroy(h->ev_counters);
     for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]);
     cudaEventDestroy(h->ev_sweep[0]); cudaEventDestroy(h->ev_sweep[1]);
     cudaStreamDestroy(h->stream); cudaStreamDestroy(h->in_stream); cudaStreamDestroy(h->out_stream); cudaStreamDestroy(h->aux_stream);
-    cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join);
+    cudaStreamDestroy(h->front_stream); cudaStreamDestroy(h->back_stream); cudaEventDestroy(h->ev_ready);
     delete h;
 }
 
@@ -608,6 +686,25 @@ int32_t gcra_rate_limit_batch16_device(gcra_engine *h, uint64_t n, const gcra_re
     return launch_batch(h, (uint32_t)n, d_req, true, now_ns, d_res, stream ? (cudaStream_t)stream : h->stream, true);
 }
 
+int32_t gcra_rate_limit_batch_device_pipelined(gcra_engine *h, uint64_t n, const gcra_request *d_req,
+                                               gcra_result *d_res, void *ready_stream) {
+    CK(cudaSetDevice(h->device));
+    cudaEvent_t ready = nullptr;
+    if (ready_stream) {
+        CK(cudaEventRecord(h->ev_ready, (cudaStream_t)ready_stream));
+        ready = h->ev_ready;
+    }
+    return launch_pipelined(h, (uint32_t)n, d_req, false, 0, d_res, ready, nullptr);
+}
+
+int32_t gcra_pipeline_join(gcra_engine *h, void *stream) {
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->ev_ready, h->back_stream));
+    if (stream) CK(cudaStreamWaitEvent((cudaStream_t)stream, h->ev_ready, 0));
+    else CK(cudaEventSynchronize(h->ev_ready));
+    return GCRA_OK;
+}
+
 static int host_batch(gcra_engine *h, uint64_t n, const void *req, size_t rsz, bool compact, int64_t now_batch,
                       gcra_result *res) {
     CK(cudaSetDevice(h->device));
@@ -706,12 +803,13 @@ int32_t gcra_ring_submit(gcra_engine *h, uint32_t slot, uint32_t n, int64_t now_
     size_t rsz = h->ring_compact ? sizeof(gcra_request16) : sizeof(gcra_request);
     CK(cudaMemcpyAsync(s.d_req, s.h_req, (size_t)n * rsz, cudaMemcpyHostToDevice, h->in_stream));
     CK(cudaEventRecord(s.ev_in, h->in_stream));
-    CK(cudaStreamWaitEvent(h->stream, s.ev_in, 0));
-    int rc = launch_batch(h, n, s.d_req, h->ring_compact, now_ns, s.d_res, h->stream, false);
+    // front half (ingest + order) of this slot overlaps the back half (decide) of the previous one
+    cudaEvent_t done = nullptr;
+    int rc = launch_pipelined(h, n, s.d_req, h->ring_compact, now_ns, s.d_res, s.ev_in, &done);
     if (rc) return rc;
-    CK(cudaEventRecord(s.ev_comp, h->stream));
-    RC(refresh_counters(h, false));
-    CK(cudaStreamWaitEvent(h->out_stream, s.ev_comp, 0));
+    if (done) CK(cudaStreamWaitEvent(h->out_stream, done, 0));
+    CK(cudaMemcpyAsync(h->h_counters, h->tab.counters, C_COUNT * sizeof(u64), cudaMemcpyDeviceToHost, h->out_stream));
+    CK(cudaEventRecord(h->ev_counters, h->out_stream));
     CK(cudaMemcpyAsync(s.h_res, s.d_res, (size_t)n * sizeof(gcra_result), cudaMemcpyDeviceToHost, h->out_stream));
     CK(cudaEventRecord(s.ev_done, h->out_stream));
     s.in_flight = true;
@@ -777,6 +875,9 @@ int32_t gcra_peek(gcra_engine *h, uint64_t key_hash, int64_t *tat, int64_t *expi
 int32_t gcra_sync(gcra_engine *h) {
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->in_stream));
+    CK(cudaStreamSynchronize(h->front_stream));
+    CK(cudaStreamSynchronize(h->back_stream));
+    CK(cudaStreamSynchronize(h->aux_stream));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaStreamSynchronize(h->out_stream));
     return GCRA_OK;

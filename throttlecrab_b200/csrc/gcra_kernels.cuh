@@ -156,7 +156,10 @@ ingest_kernel(Table t, const void *__restrict__ req_base, const PolicyDerived *_
 // ---------------------------------------------------------------------------------------------
 // K1b: stable LSD radix sort on the slot bits of (slot << 32 | index)
 // ---------------------------------------------------------------------------------------------
-constexpr int SORT_ITEMS = 4;                              // items per thread
+#ifndef GCRA_SORT_ITEMS
+#define GCRA_SORT_ITEMS 4
+#endif
+constexpr int SORT_ITEMS = GCRA_SORT_ITEMS;                // items per thread
 constexpr int SORT_TILE = TILE_THREADS * SORT_ITEMS;       // 1024 keys per CTA
 constexpr int SORT_MAX_BITS = 9;
 constexpr int SORT_MAX_DIGITS = 1 << SORT_MAX_BITS;
@@ -294,34 +297,41 @@ __device__ __forceinline__ void run_chunk(u32 lane, bool mine, u32 gmask, const 
                 mut = (so_tat != s.tat) | (so_exp != s.exp);
             }
         }
-        const u32 P = __ballot_sync(0xffffffffu, pending);
-        if (P == 0) break;
         const u32 M = __ballot_sync(0xffffffffu, pending && mut);
-        const u32 prior = M & gmask & lt;
+        const u32 prior = M & gmask & lt;                  // state-changing lanes of my run before me
+        const bool final_now = pending && prior == 0;
+        const u32 behind = __ballot_sync(0xffffffffu, pending && prior != 0);
+        if (final_now) {
+            fin = d;
+            // a write over an entry that exists but is expired (adaptive_cleanup.rs:233,267)
+            if (d.allowed && !d.live && s.exp >= 0) n_exp_hits++;
+            if (mut) { s.tat = so_tat; s.exp = so_exp; mflag = true; }
+            pending = false;
+        }
+        if (behind == 0) break;                            // common case: one pass, no shuffles
         const int src = prior ? (__ffs(prior) - 1) : (int)lane;
         const i64 sn_tat = __shfl_sync(0xffffffffu, so_tat, src);
         const i64 sn_exp = __shfl_sync(0xffffffffu, so_exp, src);
-        if (pending) {
-            if (prior == 0) {
-                fin = d;
-                // a write over an entry that exists but is expired (adaptive_cleanup.rs:233,267)
-                if (d.allowed && !d.live && s.exp >= 0) n_exp_hits++;
-                if (mut) { s.tat = so_tat; s.exp = so_exp; mflag = true; }
-                pending = false;
-            } else {
-                s.tat = sn_tat; s.exp = sn_exp;
-            }
-        }
+        if (pending) { s.tat = sn_tat; s.exp = sn_exp; }
     }
     changed_any = mflag;
 }
 
 // A run of LONG_RUN_MIN or more requests on one key (a hot key) is not walked by its warp: the warp
 // appends (first position, length) to a work list and decide_long_kernel gives it a whole CTA.
-constexpr u32 LONG_RUN_MIN = 512;     // >= this: one CTA per run (decide_long_kernel)
-constexpr u32 GIANT_RUN_MIN = 4096;   // >= this: one 8-CTA cluster per run (decide_giant_kernel)
+#ifndef GCRA_LONG_MIN
+#define GCRA_LONG_MIN 512
+#endif
+#ifndef GCRA_GIANT_MIN
+#define GCRA_GIANT_MIN 4096
+#endif
+#ifndef GCRA_CLUSTER
+#define GCRA_CLUSTER 8
+#endif
+constexpr u32 LONG_RUN_MIN = GCRA_LONG_MIN;     // >= this: one CTA per run (decide_runs_kernel<1>)
+constexpr u32 GIANT_RUN_MIN = GCRA_GIANT_MIN;   // >= this: one cluster per run (decide_runs_kernel<CLUSTER_CTAS>)
 constexpr int LONG_THREADS = 512;
-constexpr int CLUSTER_CTAS = 8;
+constexpr int CLUSTER_CTAS = GCRA_CLUSTER;
 struct LongRun { u32 start, len; };
 
 __device__ __forceinline__ void load_req(const Req *__restrict__ drec, u32 idx, Req &r) {
