@@ -206,3 +206,30 @@ def test_tight_table_stash_and_growth(batch):
     if batch == 64:
         assert s["stash_entries"] > 0             # keys really live in the stash
     assert s["table_slots"] < 4 * n_keys          # stayed tight: load well above the production 0.5
+
+
+def test_pipelined_and_mixed_submission_match_blocking():
+    """gcra_rate_limit_batch_device_pipelined (front half of batch i+1 overlapping the decide kernels of
+    batch i), mixed with in-stream batches, gives bit-identical results to blocking host batches."""
+    import torch
+    n_keys, T, n_ticks = 30_000, 1 << 14, 12
+    req = traces.config4(n_keys=n_keys, n_ticks=n_ticks, tick_size=T, hot=50)
+    ereq = engine_requests(req)
+    a = tc.RateLimiter(tc.ManualStore(capacity=n_keys, created_ns=traces.T0, max_batch=T))
+    want = a.rate_limit_batch(ereq)
+    b = tc.RateLimiter(tc.ManualStore(capacity=n_keys, created_ns=traces.T0, max_batch=T))
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.Stream(dev)
+    with torch.cuda.stream(st):
+        d_req = torch.from_numpy(ereq.view(np.uint8).reshape(n_ticks, T * 48)).to(dev)
+        d_res = torch.zeros((n_ticks, T * 32), dtype=torch.uint8, device=dev)
+        st.synchronize()
+        for t in range(n_ticks):
+            if t % 5 == 3:      # an in-stream batch in the middle of pipelined ones
+                b.rate_limit_batch_device(T, d_req[t].data_ptr(), d_res[t].data_ptr(), st.cuda_stream)
+            else:
+                b.submit_device(T, d_req[t].data_ptr(), d_res[t].data_ptr(), st.cuda_stream)
+        b.join(st.cuda_stream)
+        st.synchronize()
+    got = d_res.cpu().numpy().view(tc.RES_DTYPE).reshape(-1)
+    assert first_mismatch(want, got, req) is None, first_mismatch(want, got, req)

@@ -46,7 +46,8 @@ struct RingSlot {
 };
 }  // namespace
 
-// per-batch scratch; two sets so that the front half of one batch can overlap the back half of the previous
+// per-batch scratch; several sets so that the front halves of the next batches can overlap the back half of
+// the current one
 struct Scratch {
     Req *drec = nullptr;
     u64 *keys_a = nullptr, *keys_b = nullptr;
@@ -66,9 +67,13 @@ struct gcra_engine {
     bool tight = false;              // GCRA_FLAG_TIGHT_TABLE: tests only, exercises stash + growth
     // scratch for one batch
     uint32_t max_batch = 0;
-    Scratch scr[2];
+#ifndef GCRA_PIPE_SETS
+#define GCRA_PIPE_SETS 2
+#endif
+    static const int N_SCR = GCRA_PIPE_SETS;
+    Scratch scr[N_SCR];
     uint32_t scr_next = 0;
-    cudaStream_t front_stream = nullptr, back_stream = nullptr;   // pipelined submission
+    cudaStream_t front_stream[N_SCR] = {}, back_stream = nullptr;   // pipelined submission
     cudaEvent_t ev_ready = nullptr;
     void *d_req = nullptr;
     gcra_result *d_res = nullptr;
@@ -433,7 +438,7 @@ static int launch_batch(gcra_engine *h, uint32_t n, const void *d_req, bool comp
     if (n == 0) return GCRA_OK;
     RC(check_batch(h, n, compact));
     Scratch &sc = h->scr[h->scr_next];
-    h->scr_next ^= 1;
+    h->scr_next = (h->scr_next + 1) % gcra_engine::N_SCR;
     // order after every earlier batch (they may have been submitted pipelined on the engine's streams),
     // which also frees this scratch set
     for (auto &o : h->scr) if (o.back_recorded) CK(cudaStreamWaitEvent(st, o.ev_back, 0));
@@ -452,18 +457,18 @@ static int launch_pipelined(gcra_engine *h, uint32_t n, const void *d_req, bool 
                             gcra_result *d_res, cudaEvent_t ready, cudaEvent_t *done) {
     if (n == 0) { if (done) *done = nullptr; return GCRA_OK; }
     RC(check_batch(h, n, compact));
-    Scratch &sc = h->scr[h->scr_next];
-    h->scr_next ^= 1;
-    if (ready) CK(cudaStreamWaitEvent(h->front_stream, ready, 0));
-    if (sc.back_recorded) CK(cudaStreamWaitEvent(h->front_stream, sc.ev_back, 0));   // scratch set free again
+    const uint32_t k = h->scr_next;
+    Scratch &sc = h->scr[k];
+    h->scr_next = (h->scr_next + 1) % gcra_engine::N_SCR;
+    cudaStream_t fs = h->front_stream[k];                  // (all sets share one front stream, see gcra_create)
+    if (ready) CK(cudaStreamWaitEvent(fs, ready, 0));
+    if (sc.back_recorded) CK(cudaStreamWaitEvent(fs, sc.ev_back, 0));   // scratch set free again
     u64 *sorted = nullptr;
-    RC(enqueue_front(h, sc, n, d_req, compact, now_batch, d_res, h->front_stream, false, &sorted));
-    CK(cudaEventRecord(sc.ev_front, h->front_stream));
+    RC(enqueue_front(h, sc, n, d_req, compact, now_batch, d_res, fs, false, &sorted));
+    CK(cudaEventRecord(sc.ev_front, fs));
     CK(cudaStreamWaitEvent(h->back_stream, sc.ev_front, 0));
-    {   // decisions strictly in submission order, also after a batch submitted on a caller stream
-        Scratch &other = h->scr[h->scr_next];
-        if (other.back_recorded) CK(cudaStreamWaitEvent(h->back_stream, other.ev_back, 0));
-    }
+    // decisions strictly in submission order, also after batches submitted on a caller stream
+    for (auto &o : h->scr) if (&o != &sc && o.back_recorded) CK(cudaStreamWaitEvent(h->back_stream, o.ev_back, 0));
     RC(enqueue_back(h, sc, n, sorted, d_res, h->back_stream, false));
     CK(cudaEventRecord(sc.ev_back, h->back_stream));
     sc.back_recorded = true;
@@ -496,7 +501,10 @@ int32_t gcra_create(const gcra_config *cfg, gcra_engine **out) {
     cudaStreamCreateWithFlags(&h->in_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&h->front_stream, cudaStreamNonBlocking);
+    // ONE front stream shared by all scratch sets: front halves must not overlap each other (a key claimed
+    // by a later batch's ingest could be decided by an earlier batch before its phantom mark has landed)
+    cudaStreamCreateWithFlags(&h->front_stream[0], cudaStreamNonBlocking);
+    for (int k = 1; k < gcra_engine::N_SCR; k++) h->front_stream[k] = h->front_stream[0];
     cudaStreamCreateWithFlags(&h->back_stream, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming);
     h->capacity = cfg->capacity ? cfg->capacity : 1000;      // DEFAULT_CAPACITY adaptive_cleanup.rs:10
@@ -519,7 +527,7 @@ int32_t gcra_create(const gcra_config *cfg, gcra_engine **out) {
               cudaMallocHost(&h->h_op, 2 * sizeof(StoreOpResult)) == cudaSuccess &&
               cudaMallocHost(&h->h_counters, C_COUNT * sizeof(u64)) == cudaSuccess &&
               cudaMallocHost(&h->h_snap, (size_t)gcra_engine::N_SNAP * C_COUNT * sizeof(u64)) == cudaSuccess;
-    for (int k = 0; k < 2 && ok; k++) {
+    for (int k = 0; k < gcra_engine::N_SCR && ok; k++) {
         Scratch &sc = h->scr[k];
         ok = cudaMalloc(&sc.drec, mb * sizeof(Req)) == cudaSuccess &&
              cudaMalloc(&sc.keys_a, mb * sizeof(u64)) == cudaSuccess &&
@@ -582,7 +590,8 @@ void gcra_destroy(gcra_engine *h) {
     for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]);
     cudaEventDestroy(h->ev_sweep[0]); cudaEventDestroy(h->ev_sweep[1]);
     cudaStreamDestroy(h->stream); cudaStreamDestroy(h->in_stream); cudaStreamDestroy(h->out_stream); cudaStreamDestroy(h->aux_stream);
-    cudaStreamDestroy(h->front_stream); cudaStreamDestroy(h->back_stream); cudaEventDestroy(h->ev_ready);
+    cudaStreamDestroy(h->front_stream[0]);
+    cudaStreamDestroy(h->back_stream); cudaEventDestroy(h->ev_ready);
     delete h;
 }
 
@@ -875,7 +884,7 @@ int32_t gcra_peek(gcra_engine *h, uint64_t key_hash, int64_t *tat, int64_t *expi
 int32_t gcra_sync(gcra_engine *h) {
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->in_stream));
-    CK(cudaStreamSynchronize(h->front_stream));
+    CK(cudaStreamSynchronize(h->front_stream[0]));
     CK(cudaStreamSynchronize(h->back_stream));
     CK(cudaStreamSynchronize(h->aux_stream));
     CK(cudaStreamSynchronize(h->stream));
