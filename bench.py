@@ -291,7 +291,7 @@ def main():
         lim.rate_limit_batch_device(TICK, d_req[W].data_ptr(), extra.data_ptr(), stream.cuda_stream)
         torch.cuda.synchronize()
         phases = store.last_kernel_ms()
-    clocks = sampler.stop() if rank == 0 else None
+    # (the clock sampler keeps running through the e2e region: the kernel-only region lasts only a few ms)
 
     # ---------------------------------------------------------------- e2e through the pinned ring
     e2e = None
@@ -302,8 +302,9 @@ def main():
         for a in range(0, n_keys, TICK):
             lim2.rate_limit_batch(warm[a:a + TICK])
         del warm
-        ring = tc.Ring(lim2, slots=W + K, slot_capacity=TICK)
-        for i in range(W + K):
+        KE = min(K, 32)          # every step owns a pinned 80-MiB slot: cap the pinned memory at ~3 GB
+        ring = tc.Ring(lim2, slots=W + KE, slot_capacity=TICK)
+        for i in range(W + KE):
             ring.req[i][:] = ticks[i * TICK:(i + 1) * TICK]      # requests sit in pinned host memory
         for i in range(W):
             ring.submit(i, TICK)
@@ -311,16 +312,16 @@ def main():
             ring.wait(i)
         store2.sync()
         t_a = time.perf_counter()
-        for i in range(W, W + K):
+        for i in range(W, W + KE):
             ring.submit(i, TICK)
-        for i in range(W, W + K):
+        for i in range(W, W + KE):
             ring.wait(i)
         t_b = time.perf_counter()
-        e2e_val = K * TICK / (t_b - t_a)
-        got = np.concatenate([ring.res[i] for i in range(W, W + K)])
-        same = got.tobytes() == res_np.reshape(-1).tobytes()
+        e2e_val = KE * TICK / (t_b - t_a)
+        got = np.concatenate([ring.res[i] for i in range(W, W + KE)])
+        same = got.tobytes() == res_np[:KE].reshape(-1).tobytes()
         e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": TICK * 48, "d2h_bytes_per_step": TICK * 32,
-               "api": "gcra_ring_submit/gcra_ring_wait, pinned host ring, 48-byte requests",
+               "api": "gcra_ring_submit/gcra_ring_wait, pinned host ring, 48-byte requests", "steps": KE,
                "matches_kernel_only_results": bool(same)}
         del ring
         # extra: compact 16-byte requests (policy table + per-call now), same ticks, same results
@@ -335,8 +336,8 @@ def main():
             for a in range(0, n_keys, TICK):
                 lim3.rate_limit_batch(warm[a:a + TICK])
             del warm
-            ring16 = tc.Ring(lim3, slots=W + K, slot_capacity=TICK, compact=True)
-            for i in range(W + K):
+            ring16 = tc.Ring(lim3, slots=W + KE, slot_capacity=TICK, compact=True)
+            for i in range(W + KE):
                 sl = ticks[i * TICK:(i + 1) * TICK]
                 r16 = ring16.req[i]
                 r16["key_hash"] = sl["key_hash"]
@@ -346,22 +347,22 @@ def main():
                     m = (sl["max_burst"] == p[0]) & (sl["count_per_period"] == p[1]) & (sl["period"] == p[2])
                     pidx[m] = j
                 r16["policy"] = pidx
-            nows = [int(ticks["now_ns"][i * TICK]) for i in range(W + K)]
+            nows = [int(ticks["now_ns"][i * TICK]) for i in range(W + KE)]
             for i in range(W):
                 ring16.submit(i, TICK, nows[i])
             for i in range(W):
                 ring16.wait(i)
             store3.sync()
             t_a = time.perf_counter()
-            for i in range(W, W + K):
+            for i in range(W, W + KE):
                 ring16.submit(i, TICK, nows[i])
-            for i in range(W, W + K):
+            for i in range(W, W + KE):
                 ring16.wait(i)
             t_b = time.perf_counter()
-            got16 = np.concatenate([ring16.res[i] for i in range(W, W + K)])
-            e2e["compact_requests"] = {"value": K * TICK / (t_b - t_a), "unit": UNIT, "h2d_bytes_per_step": TICK * 16,
+            got16 = np.concatenate([ring16.res[i] for i in range(W, W + KE)])
+            e2e["compact_requests"] = {"value": KE * TICK / (t_b - t_a), "unit": UNIT, "h2d_bytes_per_step": TICK * 16,
                                        "d2h_bytes_per_step": TICK * 32,
-                                       "matches_kernel_only_results": bool(got16.tobytes() == res_np.reshape(-1).tobytes())}
+                                       "matches_kernel_only_results": bool(got16.tobytes() == res_np[:KE].reshape(-1).tobytes())}
             del ring16
             store3.close()
         except Exception as ex:      # the extra must never cost the main line
@@ -411,6 +412,8 @@ def main():
                "d2h_bytes_per_step": TICK * 32,
                "api": "per rank: pinned host -> H2D -> ShardedLimiter.submit (partition, all-to-all, decide, all-to-all, "
                       "unpermute) -> D2H to pinned host, copies on their own streams"}
+
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N=1)
     cpu = None
