@@ -174,6 +174,10 @@ uint64_t gcra_len(gcra_engine *h);
 int32_t gcra_get_stats(gcra_engine *h, gcra_stats *out);
 /* table entry of a key after the fact: returns found, tat and expiry (saturated to INT64_MAX) */
 int32_t gcra_peek(gcra_engine *h, uint64_t key_hash, int64_t *tat, int64_t *expiry_ns, uint8_t *found);
+/* dump the table to a file / load it back (the reference keeps its state in memory only and loses it on
+ * restart); decisions after a load are identical to those of the engine that saved */
+int32_t gcra_snapshot_save(gcra_engine *h, const char *path);
+int32_t gcra_snapshot_load(gcra_engine *h, const char *path);
 /* block until all device work of this handle has finished */
 int32_t gcra_sync(gcra_engine *h);
 /* device time (ms) of the kernels of the most recent batch call, measured with CUDA events on

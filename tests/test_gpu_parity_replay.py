@@ -233,3 +233,29 @@ def test_pipelined_and_mixed_submission_match_blocking():
         st.synchronize()
     got = d_res.cpu().numpy().view(tc.RES_DTYPE).reshape(-1)
     assert first_mismatch(want, got, req) is None, first_mismatch(want, got, req)
+
+
+def test_snapshot_restore_continues_identically(tmp_path):
+    """gcra_snapshot_save / _load: an engine restarted from a snapshot (even one created with another
+    capacity) continues with exactly the answers of the oracle that never stopped."""
+    n_keys = 8000
+    req = traces.config1(n=60_000, keys=n_keys)
+    ereq = engine_requests(req)
+    want = oracle.OracleStore(oracle.PERIODIC, capacity=n_keys, created_ns=traces.T0, p0=10**9).replay(req)
+    a = tc.RateLimiter(tc.ManualStore(capacity=n_keys, created_ns=traces.T0, max_batch=4096))
+    got = np.empty(len(req), tc.RES_DTYPE)
+    half = 30_000
+    for s in range(0, half, 4096):
+        e = min(s + 4096, half)
+        a.rate_limit_batch(ereq[s:e], out=got[s:e])
+    path = str(tmp_path / "table.gcra")
+    a.store.save(path)
+    len_before = a.store.len()
+    a.store.close()
+    b = tc.RateLimiter(tc.ManualStore(capacity=100, created_ns=traces.T0, max_batch=4096))   # other geometry
+    b.store.load(path)
+    assert b.store.len() == len_before
+    for s in range(half, len(req), 4096):
+        e = min(s + 4096, len(req))
+        b.rate_limit_batch(ereq[s:e], out=got[s:e])
+    assert first_mismatch(want, got, req) is None, first_mismatch(want, got, req)

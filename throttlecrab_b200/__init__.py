@@ -14,6 +14,7 @@ All state and all decisions live on the GPU behind the C ABI (include/gcra_b200.
 module only marshals arguments.  There is no CPU fallback.
 """
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -181,6 +182,12 @@ class _GpuStore:
         t, e, f = C.c_int64(), C.c_int64(), C.c_uint8()
         self._check(self._L.gcra_peek(self._h, key_hash, C.byref(t), C.byref(e), C.byref(f)))
         return (t.value, e.value) if f.value else None
+
+    def save(self, path):
+        self._check(self._L.gcra_snapshot_save(self._h, os.fsencode(path)))
+
+    def load(self, path):
+        self._check(self._L.gcra_snapshot_load(self._h, os.fsencode(path)))
 
     def sync(self):
         self._check(self._L.gcra_sync(self._h))

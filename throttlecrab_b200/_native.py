@@ -93,6 +93,8 @@ SYMBOLS = {
     "gcra_len": (_u64, [_vp]),
     "gcra_get_stats": (_i32, [_vp, C.POINTER(Stats)]),
     "gcra_peek": (_i32, [_vp, _u64, _pi64, _pi64, _pu8]),
+    "gcra_snapshot_save": (_i32, [_vp, C.c_char_p]),
+    "gcra_snapshot_load": (_i32, [_vp, C.c_char_p]),
     "gcra_sync": (_i32, [_vp]),
     "gcra_last_kernel_ms": (_i32, [_vp, C.POINTER(C.c_float * 4)]),
     "gcra_last_sweep_ms": (_i32, [_vp, C.POINTER(C.c_float)]),

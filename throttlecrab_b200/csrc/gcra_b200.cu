@@ -911,6 +911,97 @@ int32_t gcra_last_sweep_ms(gcra_engine *h, float *ms) {
 
 uint64_t gcra_launch_count(gcra_engine *h) { return h->launches; }
 
+// ---- snapshot / restore (absent in the reference: its state is lost on restart) -----------
+namespace {
+struct SnapshotHeader {
+    char magic[8];
+    uint32_t version, total_lines, nb_main, stash_slots;
+    uint64_t capacity;
+    uint64_t counters[C_COUNT];
+};
+const char SNAP_MAGIC[8] = {'G', 'C', 'R', 'A', 'B', '2', '0', '0'};
+const size_t SNAP_CHUNK = 32u << 20;
+}  // namespace
+
+static int copy_to_file(gcra_engine *h, FILE *f, const void *dptr, size_t bytes, std::vector<char> &buf) {
+    for (size_t off = 0; off < bytes; off += SNAP_CHUNK) {
+        size_t m = std::min(SNAP_CHUNK, bytes - off);
+        CK(cudaMemcpy(buf.data(), (const char *)dptr + off, m, cudaMemcpyDeviceToHost));
+        if (fwrite(buf.data(), 1, m, f) != m) { h->err = "snapshot: short write"; return GCRA_INTERNAL; }
+    }
+    return GCRA_OK;
+}
+
+static int copy_from_file(gcra_engine *h, FILE *f, void *dptr, size_t bytes, std::vector<char> &buf) {
+    for (size_t off = 0; off < bytes; off += SNAP_CHUNK) {
+        size_t m = std::min(SNAP_CHUNK, bytes - off);
+        if (fread(buf.data(), 1, m, f) != m) { h->err = "snapshot: short read"; return GCRA_INTERNAL; }
+        CK(cudaMemcpy((char *)dptr + off, buf.data(), m, cudaMemcpyHostToDevice));
+    }
+    return GCRA_OK;
+}
+
+int32_t gcra_snapshot_save(gcra_engine *h, const char *path) {
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    FILE *f = fopen(path, "wb");
+    if (!f) { h->err = std::string("snapshot: cannot open ") + path; return GCRA_INTERNAL; }
+    SnapshotHeader hd{};
+    memcpy(hd.magic, SNAP_MAGIC, 8);
+    hd.version = 1; hd.total_lines = h->total_lines; hd.nb_main = h->tab.nb_main; hd.stash_slots = h->tab.stash_slots;
+    hd.capacity = h->capacity;
+    int rc = GCRA_OK;
+    if (cudaMemcpy(hd.counters, h->tab.counters, sizeof(hd.counters), cudaMemcpyDeviceToHost) != cudaSuccess ||
+        fwrite(&hd, sizeof(hd), 1, f) != 1) { h->err = "snapshot: header"; rc = GCRA_INTERNAL; }
+    std::vector<char> buf(SNAP_CHUNK);
+    const size_t slots = (size_t)h->total_lines * 4;
+    if (!rc) rc = copy_to_file(h, f, h->tab.keys, slots * sizeof(u64), buf);
+    if (!rc) rc = copy_to_file(h, f, h->tab.state, slots * sizeof(TatOff), buf);
+    if (!rc) rc = copy_to_file(h, f, h->tab.ei, slots * sizeof(i64), buf);
+    if (fclose(f) != 0 && !rc) { h->err = "snapshot: close"; rc = GCRA_INTERNAL; }
+    return rc;
+}
+
+int32_t gcra_snapshot_load(gcra_engine *h, const char *path) {
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    FILE *f = fopen(path, "rb");
+    if (!f) { h->err = std::string("snapshot: cannot open ") + path; return GCRA_INTERNAL; }
+    SnapshotHeader hd{};
+    if (fread(&hd, sizeof(hd), 1, f) != 1 || memcmp(hd.magic, SNAP_MAGIC, 8) != 0 || hd.version != 1) {
+        fclose(f); h->err = "snapshot: bad header"; return GCRA_INTERNAL;
+    }
+    int rc = GCRA_OK;
+    if (hd.total_lines != h->total_lines || hd.nb_main != h->tab.nb_main || hd.stash_slots != h->tab.stash_slots) {
+        // other geometry: replace the table by one of the snapshot's shape
+        uint32_t tl, nb, ss;
+        table_geometry(hd.capacity, h->tight, tl, nb, ss);
+        if (tl != hd.total_lines || nb != hd.nb_main || ss != hd.stash_slots) {
+            fclose(f); h->err = "snapshot: geometry not reproducible with this build/flags"; return GCRA_INTERNAL;
+        }
+        Table nt{};
+        uint32_t nl = 0;
+        rc = alloc_table(h, hd.capacity, nt, nl, h->tab.counters);
+        if (rc) { fclose(f); return rc; }
+        CK(cudaStreamSynchronize(h->stream));
+        cudaFree(h->tab.keys); cudaFree(h->tab.state); cudaFree(h->tab.ei);
+        h->tab = nt; h->total_lines = nl; h->capacity = hd.capacity;
+    }
+    std::vector<char> buf(SNAP_CHUNK);
+    const size_t slots = (size_t)h->total_lines * 4;
+    if (!rc) rc = copy_from_file(h, f, h->tab.keys, slots * sizeof(u64), buf);
+    if (!rc) rc = copy_from_file(h, f, h->tab.state, slots * sizeof(TatOff), buf);
+    if (!rc) rc = copy_from_file(h, f, h->tab.ei, slots * sizeof(i64), buf);
+    fclose(f);
+    if (rc) return rc;
+    CK(cudaMemcpy(h->tab.counters, hd.counters, sizeof(hd.counters), cudaMemcpyHostToDevice));
+    h->occupied_ub = hd.counters[C_OCCUPIED];
+    h->seen_allowed = hd.counters[C_ALLOWED];
+    h->seen_expired_hits = hd.counters[C_EXPIRED_HITS];
+    for (int i = 0; i < gcra_engine::N_SNAP; i++) h->snap_used[i] = false;
+    return GCRA_OK;
+}
+
 // ---- routing -------------------------------------------------------------------------------------
 uint32_t gcra_owner_of(uint64_t key_hash, uint32_t n_shards) { return owner_of(key_hash, n_shards); }
 
