@@ -164,6 +164,33 @@ constexpr int SORT_TILE = TILE_THREADS * SORT_ITEMS;       // 1024 keys per CTA
 constexpr int SORT_MAX_BITS = 9;
 constexpr int SORT_MAX_DIGITS = 1 << SORT_MAX_BITS;
 
+// block-wide exclusive scan of one value per thread (warp shuffles + one shared-memory hop);
+// returns the exclusive prefix, the block total in *total
+__device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32 *part, u32 *total) {
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (u32)o) inc += t;
+    }
+    if (lane == 31) part[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        u32 w = lane < TILE_THREADS / 32 ? part[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < TILE_THREADS / 32; o <<= 1) {
+            u32 t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= (u32)o) w += t;
+        }
+        if (lane < TILE_THREADS / 32) part[lane] = w;          // inclusive over warps
+    }
+    __syncthreads();
+    const u32 before = warp > 0 ? part[warp - 1] : 0;
+    *total = part[TILE_THREADS / 32 - 1];
+    return before + inc - v;
+}
+
 __global__ void __launch_bounds__(TILE_THREADS)
 sort_hist_kernel(const u64 *__restrict__ in, u32 n, u32 shift, u32 bits, u32 num_tiles,
                  u32 *__restrict__ hist) {
@@ -184,24 +211,16 @@ sort_hist_kernel(const u64 *__restrict__ in, u32 n, u32 shift, u32 bits, u32 num
 // one CTA per digit: exclusive scan of that digit's per-tile counts, digit total to tot[d]
 __global__ void __launch_bounds__(TILE_THREADS)
 sort_rowscan_kernel(u32 *__restrict__ hist, u32 num_tiles, u32 *__restrict__ tot) {
-    __shared__ u32 part[TILE_THREADS];
+    __shared__ u32 part[TILE_THREADS / 32];
     u32 *row = hist + (size_t)blockIdx.x * num_tiles;
     const u32 per = (num_tiles + TILE_THREADS - 1) / TILE_THREADS;
     const u32 lo = min(threadIdx.x * per, num_tiles), hi = min(lo + per, num_tiles);
     u32 s = 0;
     for (u32 i = lo; i < hi; i++) s += row[i];
-    part[threadIdx.x] = s;
-    __syncthreads();
-    // block exclusive scan (Hillis-Steele on 256 partials)
-    for (u32 off = 1; off < TILE_THREADS; off <<= 1) {
-        u32 v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
-        __syncthreads();
-        part[threadIdx.x] += v;
-        __syncthreads();
-    }
-    u32 acc = part[threadIdx.x] - s;
+    u32 total;
+    u32 acc = block_exclusive_scan(s, part, &total);
     for (u32 i = lo; i < hi; i++) { u32 v = row[i]; row[i] = acc; acc += v; }
-    if (threadIdx.x == TILE_THREADS - 1) tot[blockIdx.x] = part[TILE_THREADS - 1];
+    if (threadIdx.x == 0) tot[blockIdx.x] = total;
 }
 
 __global__ void __launch_bounds__(TILE_THREADS)
@@ -212,25 +231,20 @@ sort_scatter_kernel(const u64 *__restrict__ in, u64 *__restrict__ outk, u32 n, u
     __shared__ u32 gbase[SORT_MAX_DIGITS];     // global base of (digit, this tile)
     const u32 nd = 1u << bits, mask = nd - 1;
     const u32 w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ u32 part[NW];
     for (u32 d = threadIdx.x; d < nd; d += TILE_THREADS) {
 #pragma unroll
         for (int x = 0; x < NW; x++) cnt[x][d] = 0;
-        gbase[d] = tot[d];
+    }
+    {   // exclusive scan of the digit totals (nd <= 512: two consecutive digits per thread)
+        const u32 d0 = 2 * threadIdx.x, d1 = d0 + 1;
+        const u32 t0 = d0 < nd ? tot[d0] : 0, t1 = d1 < nd ? tot[d1] : 0;
+        u32 total;
+        const u32 ex = block_exclusive_scan(t0 + t1, part, &total);
+        if (d0 < nd) gbase[d0] = ex + hist[(size_t)d0 * num_tiles + blockIdx.x];
+        if (d1 < nd) gbase[d1] = ex + t0 + hist[(size_t)d1 * num_tiles + blockIdx.x];
     }
     __syncthreads();
-    // exclusive scan of the digit totals (Hillis-Steele, nd <= 512, two elements per thread)
-    for (u32 off = 1; off < nd; off <<= 1) {
-        u32 v0 = 0, v1 = 0;
-        u32 d0 = threadIdx.x, d1 = threadIdx.x + TILE_THREADS;
-        if (d0 < nd && d0 >= off) v0 = gbase[d0 - off];
-        if (d1 < nd && d1 >= off) v1 = gbase[d1 - off];
-        __syncthreads();
-        if (d0 < nd) gbase[d0] += v0;
-        if (d1 < nd) gbase[d1] += v1;
-        __syncthreads();
-    }
-    for (u32 d = threadIdx.x; d < nd; d += TILE_THREADS)
-        gbase[d] = gbase[d] - tot[d] + hist[(size_t)d * num_tiles + blockIdx.x];
     // warp w owns tile elements [w*128, w*128+128): item k, lane l -> w*128 + k*32 + l (index order)
     const u32 base = blockIdx.x * SORT_TILE + w * (32 * SORT_ITEMS);
     u64 key[SORT_ITEMS];
