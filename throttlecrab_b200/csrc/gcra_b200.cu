@@ -404,7 +404,7 @@ static int enqueue_front(gcra_engine *h, Scratch &sc, uint32_t n, const void *d_
 static int enqueue_back(gcra_engine *h, Scratch &sc, uint32_t n, const u64 *src, gcra_result *d_res, cudaStream_t st,
                         bool timed) {
     const uint32_t warps = (n + 31) / 32;
-    decide_kernel<<<(warps + TILE_THREADS / 32 - 1) / (TILE_THREADS / 32), TILE_THREADS, 0, st>>>(
+    decide_kernel<<<(warps + DECIDE_THREADS / 32 - 1) / (DECIDE_THREADS / 32), DECIDE_THREADS, 0, st>>>(
         h->tab, src, sc.drec, n, d_res, sc.long_runs, sc.giant_runs, sc.long_count);
     h->launches++;
     if (n >= GIANT_RUN_MIN) {
@@ -788,7 +788,9 @@ int32_t gcra_ring_create(gcra_engine *h, uint32_t slots, uint32_t slot_capacity,
     size_t rsz = compact ? sizeof(gcra_request16) : sizeof(gcra_request);
     h->ring.resize(slots);
     for (auto &s : h->ring) {
-        CK(cudaMallocHost(&s.h_req, slot_capacity * rsz));
+        // request slots are only WRITTEN by the host: optionally write-combined pinned memory (GCRA_RING_WC=1)
+        CK(cudaHostAlloc(&s.h_req, slot_capacity * rsz,
+                         getenv("GCRA_RING_WC") && atoi(getenv("GCRA_RING_WC")) ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
         CK(cudaMallocHost(&s.h_res, slot_capacity * sizeof(gcra_result)));
         CK(cudaMalloc(&s.d_req, slot_capacity * rsz));
         CK(cudaMalloc(&s.d_res, slot_capacity * sizeof(gcra_result)));

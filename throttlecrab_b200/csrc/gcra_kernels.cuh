@@ -334,7 +334,7 @@ __device__ __forceinline__ void run_chunk(u32 lane, bool mine, u32 gmask, const 
 // A run of LONG_RUN_MIN or more requests on one key (a hot key) is not walked by its warp: the warp
 // appends (first position, length) to a work list and decide_long_kernel gives it a whole CTA.
 #ifndef GCRA_LONG_MIN
-#define GCRA_LONG_MIN 512
+#define GCRA_LONG_MIN 256
 #endif
 #ifndef GCRA_GIANT_MIN
 #define GCRA_GIANT_MIN 4096
@@ -384,12 +384,17 @@ __device__ __forceinline__ void store_state(const Table &t, u32 slot, const RunS
     if (created) t.ei[slot] = s.ei;
 }
 
-__global__ void __launch_bounds__(TILE_THREADS, 4)
+#ifndef GCRA_DECIDE_THREADS
+#define GCRA_DECIDE_THREADS 256
+#endif
+constexpr int DECIDE_THREADS = GCRA_DECIDE_THREADS;   // warps are independent: the CTA size only sets scheduling granularity
+
+__global__ void __launch_bounds__(DECIDE_THREADS, 1024 / DECIDE_THREADS)
 decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ drec, u32 n,
               gcra_result *__restrict__ out, LongRun *__restrict__ long_runs, LongRun *__restrict__ giant_runs,
               u32 *__restrict__ long_count) {
     const u32 lane = threadIdx.x & 31;
-    const u32 warp_global = (blockIdx.x * TILE_THREADS + threadIdx.x) >> 5;
+    const u32 warp_global = (blockIdx.x * DECIDE_THREADS + threadIdx.x) >> 5;
     const u32 base = warp_global * 32;
     if (base >= n) return;   // whole warp
 
