@@ -203,8 +203,11 @@ def main():
         ticks = build_requests(tc, key_hash_of, tr)
         del tr
     else:
-        from throttlecrab_b200.sharded import ShardedLimiter
-        sh = ShardedLimiter(lim, dist, dev)
+        from throttlecrab_b200.sharded import NativeShardedLimiter, ShardedLimiter
+        # default: the native pipeline (one C call per tick, NCCL inside the library); GCRA_SHARD_PY=1 selects
+        # the torch.distributed implementation of the same stages
+        native_shard = os.environ.get("GCRA_SHARD_PY", "0") != "1"
+        sh = NativeShardedLimiter(lim, dist, dev) if native_shard else ShardedLimiter(lim, dist, dev)
         # warm pass through the sharded path: rank r submits keys [r*10M, (r+1)*10M), owners insert them
         stream0 = torch.cuda.Stream(dev)
         torch.cuda.set_stream(stream0)
@@ -381,7 +384,8 @@ def main():
         drs = [torch.empty(TICK * 32, dtype=torch.uint8, device=dev) for _ in range(K)]
         s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         sh.finish()
-        sh.pop_returned()
+        if not native_shard:
+            sh.pop_returned()
         torch.cuda.synchronize()
         dist.barrier()
         t_a = time.perf_counter()
@@ -389,19 +393,34 @@ def main():
         for i in range(K):
             with torch.cuda.stream(s_in):                     # H2D of tick i overlaps earlier ticks
                 dqs[i].copy_(h_req[i], non_blocking=True)
-            stream.wait_stream(s_in)
-            sh.submit(dqs[i], drs[i])
-            for ev in sh.pop_returned():                      # D2H of every tick whose results are on the way
+            if native_shard:
+                sh.submit(dqs[i], drs[i], ready_stream=s_in.cuda_stream)
+                if i >= 1:                                    # tick i-1's way back was issued inside submit(i)
+                    sh.wait_tick(1, s_out)
+                    with torch.cuda.stream(s_out):
+                        h_res[copied].copy_(drs[copied], non_blocking=True)
+                    copied += 1
+            else:
+                stream.wait_stream(s_in)
+                sh.submit(dqs[i], drs[i])
+                for ev in sh.pop_returned():                  # D2H of every tick whose results are on the way
+                    s_out.wait_event(ev)
+                    with torch.cuda.stream(s_out):
+                        h_res[copied].copy_(drs[copied], non_blocking=True)
+                    copied += 1
+        sh.finish()
+        if native_shard:
+            s_out.wait_stream(stream)
+            with torch.cuda.stream(s_out):
+                while copied < K:
+                    h_res[copied].copy_(drs[copied], non_blocking=True)
+                    copied += 1
+        else:
+            for ev in sh.pop_returned():
                 s_out.wait_event(ev)
                 with torch.cuda.stream(s_out):
                     h_res[copied].copy_(drs[copied], non_blocking=True)
                 copied += 1
-        sh.finish()
-        for ev in sh.pop_returned():
-            s_out.wait_event(ev)
-            with torch.cuda.stream(s_out):
-                h_res[copied].copy_(drs[copied], non_blocking=True)
-            copied += 1
         stream.wait_stream(s_out)
         torch.cuda.synchronize()
         dist.barrier()
@@ -448,6 +467,7 @@ def main():
                                 "%dM keys hash-sharded over %d GPUs, Zipf-1.0 stream, 2^20 requests per GPU per tick, "
                                 "stable partition + NCCL all-to-all routing (BASELINE configs[4] shape)"
                                 % (n_keys // 1_000_000, world)),
+                   "sharded_pipeline": (None if world == 1 else ("native (gcra_shard_submit)" if native_shard else "torch.distributed")),
                    "keys": n_keys, "tick": TICK, "request_bytes": 48, "result_bytes": 32,
                    "l2": "no flush: table %.2f GB and a distinct 80 MB tick per step exceed the 126 MB L2"
                          % (store.stats()["table_slots"] * 32 / 1e9),

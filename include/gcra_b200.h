@@ -201,6 +201,22 @@ int32_t gcra_route_partition(gcra_engine *h, uint64_t n, const gcra_request *d_r
 int32_t gcra_route_unpermute(gcra_engine *h, uint64_t n, const gcra_result *d_res_routed,
                              const uint32_t *d_src_index, gcra_result *d_res, void *stream);
 
+/* ---- the whole sharded tick in native code: one call per tick ------------------------------------------
+ * Partition by owner -> count exchange -> request all-to-all -> engine kernels (pipelined) -> result
+ * all-to-all -> un-permutation, on three streams with one NCCL communicator per stage (NCCL is resolved
+ * with dlopen("libnccl.so.2") at the first call).  Rank 0 creates three ncclUniqueIds
+ * (gcra_shard_unique_ids, 3 x 128 bytes), the caller broadcasts them to all ranks by whatever means it
+ * has, and every rank calls gcra_shard_init.  Within a tick, rank r's rows precede rank r+1's; ticks are
+ * decided in submission order.  d_res is complete once gcra_shard_join() has made `stream` wait (NULL =
+ * block the host). */
+int32_t gcra_shard_unique_ids(void *out_3x128);
+int32_t gcra_shard_init(gcra_engine *h, int32_t rank, int32_t world, const void *ids_3x128, uint32_t max_rows);
+int32_t gcra_shard_submit(gcra_engine *h, uint64_t n, const gcra_request *d_req, gcra_result *d_res,
+                          void *ready_stream);
+int32_t gcra_shard_join(gcra_engine *h, void *stream);
+/* make `stream` wait for the results of the tick submitted `ticks_back` submissions ago (0 = latest, < 3) */
+int32_t gcra_shard_wait_tick(gcra_engine *h, uint32_t ticks_back, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

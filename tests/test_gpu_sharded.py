@@ -25,7 +25,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n_keys, n_ticks, tick, ret):
+def _worker(rank, world, port, n_keys, n_ticks, tick, ret, native=False):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
@@ -33,10 +33,10 @@ def _worker(rank, world, port, n_keys, n_ticks, tick, ret):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     import throttlecrab_b200 as tc
     import traces
-    from throttlecrab_b200.sharded import ShardedLimiter
+    from throttlecrab_b200.sharded import NativeShardedLimiter, ShardedLimiter
     key_hash_of = tc.hash_key_ids(np.arange(n_keys, dtype=np.uint64))
     lim = tc.RateLimiter(tc.ManualStore(capacity=n_keys, device=rank, created_ns=traces.T0, max_batch=2 * tick))
-    sh = ShardedLimiter(lim, dist, dev)
+    sh = NativeShardedLimiter(lim, dist, dev) if native else ShardedLimiter(lim, dist, dev)
     glob = traces.config4(n_keys=n_keys, n_ticks=n_ticks, tick_size=tick * world, hot=20)
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
@@ -59,7 +59,8 @@ def _worker(rank, world, port, n_keys, n_ticks, tick, ret):
 
 
 @pytest.mark.timeout(600)
-def test_two_gpu_sharded_matches_single_oracle():
+@pytest.mark.parametrize("native", [False, True], ids=["torch_distributed", "native_nccl"])
+def test_two_gpu_sharded_matches_single_oracle(native):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import oracle
@@ -67,7 +68,7 @@ def test_two_gpu_sharded_matches_single_oracle():
     world, n_keys, n_ticks, tick = 2, 50_000, 6, 1 << 16
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), n_keys, n_ticks, tick, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n_keys, n_ticks, tick, ret, native), nprocs=world, join=True)
     glob = traces.config4(n_keys=n_keys, n_ticks=n_ticks, tick_size=tick * world, hot=20)
     want = oracle.OracleStore(oracle.PERIODIC, capacity=n_keys, created_ns=traces.T0, p0=10**9).replay(glob)
     got = np.empty(len(glob), oracle.RES_DTYPE)

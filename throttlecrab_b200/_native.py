@@ -16,7 +16,7 @@ _SRC = os.path.join(_PKG, "csrc")
 SO_PATH = os.environ.get("GCRA_SO") or os.path.join(_PKG, "libgcra_b200.so")   # GCRA_SO: tuning variants
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "--shared", "-Xcompiler", "-fPIC"]
+              "--shared", "-Xcompiler", "-fPIC", "-ldl"]
 
 REQ_DTYPE = np.dtype([("key_hash", "<u8"), ("max_burst", "<i8"), ("count_per_period", "<i8"),
                       ("period", "<i8"), ("quantity", "<i8"), ("now_ns", "<i8")])
@@ -99,6 +99,11 @@ SYMBOLS = {
     "gcra_last_kernel_ms": (_i32, [_vp, C.POINTER(C.c_float * 4)]),
     "gcra_last_sweep_ms": (_i32, [_vp, C.POINTER(C.c_float)]),
     "gcra_launch_count": (_u64, [_vp]),
+    "gcra_shard_unique_ids": (_i32, [_vp]),
+    "gcra_shard_init": (_i32, [_vp, _i32, _i32, _vp, _u32]),
+    "gcra_shard_submit": (_i32, [_vp, _u64, _vp, _vp, _vp]),
+    "gcra_shard_join": (_i32, [_vp, _vp]),
+    "gcra_shard_wait_tick": (_i32, [_vp, _u32, _vp]),
     "gcra_owner_of": (_u32, [_u64, _u32]),
     "gcra_route_partition": (_i32, [_vp, _u64, _vp, _u32, _vp, _vp, _vp, _vp]),
     "gcra_route_unpermute": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp]),

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <dlfcn.h>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -45,6 +46,78 @@ struct RingSlot {
     bool in_flight = false;
 };
 }  // namespace
+
+// ---- NCCL, resolved at run time (dlopen) so that single-GPU users do not need it ---------------------
+// Minimal declarations of the public NCCL API used here (nccl.h: ncclUniqueId is 128 opaque bytes,
+// ncclUint8 = 1, ncclUint32 = 3).
+namespace nccl_rt {
+struct UniqueId { char internal[128]; };
+typedef void *Comm;
+typedef int (*GetUniqueId_t)(UniqueId *);
+typedef int (*CommInitRank_t)(Comm *, int, UniqueId, int);
+typedef int (*CommDestroy_t)(Comm);
+typedef int (*Group_t)();
+typedef int (*Send_t)(const void *, size_t, int, int, Comm, cudaStream_t);
+typedef int (*Recv_t)(void *, size_t, int, int, Comm, cudaStream_t);
+typedef const char *(*ErrStr_t)(int);
+struct Api {
+    void *lib = nullptr;
+    GetUniqueId_t GetUniqueId = nullptr;
+    CommInitRank_t CommInitRank = nullptr;
+    CommDestroy_t CommDestroy = nullptr;
+    Group_t GroupStart = nullptr, GroupEnd = nullptr;
+    Send_t Send = nullptr;
+    Recv_t Recv = nullptr;
+    ErrStr_t GetErrorString = nullptr;
+};
+static Api g_api;
+static bool load() {
+    if (g_api.lib) return true;
+    void *l = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!l) l = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!l) return false;
+    Api a;
+    a.lib = l;
+    a.GetUniqueId = (GetUniqueId_t)dlsym(l, "ncclGetUniqueId");
+    a.CommInitRank = (CommInitRank_t)dlsym(l, "ncclCommInitRank");
+    a.CommDestroy = (CommDestroy_t)dlsym(l, "ncclCommDestroy");
+    a.GroupStart = (Group_t)dlsym(l, "ncclGroupStart");
+    a.GroupEnd = (Group_t)dlsym(l, "ncclGroupEnd");
+    a.Send = (Send_t)dlsym(l, "ncclSend");
+    a.Recv = (Recv_t)dlsym(l, "ncclRecv");
+    a.GetErrorString = (ErrStr_t)dlsym(l, "ncclGetErrorString");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.GroupStart || !a.GroupEnd || !a.Send || !a.Recv) return false;
+    g_api = a;
+    return true;
+}
+const int kUint8 = 1, kUint32 = 3;
+}  // namespace nccl_rt
+
+// one tick in flight through the sharded pipeline
+struct ShardSlot {
+    gcra_request *routed = nullptr, *recv_req = nullptr;
+    gcra_result *recv_res = nullptr, *back_res = nullptr;
+    u32 *src_index = nullptr;
+    u32 *counts_dev = nullptr;     // [2*W]: rows I send to every peer, rows every peer sends me
+    u32 *counts_host = nullptr;    // pinned copy
+    cudaEvent_t ev_ready = nullptr, ev_counts = nullptr, ev_routed = nullptr, ev_done = nullptr;
+    bool used = false;
+    uint32_t n = 0, n_recv = 0;
+    gcra_result *d_res_user = nullptr;
+    std::vector<size_t> send, recv, send_off, recv_off;
+};
+
+struct Shard {
+    static const int DEPTH = 4;
+    int rank = 0, world = 0;
+    uint32_t max_rows = 0;
+    nccl_rt::Comm comm_counts = nullptr, comm_req = nullptr, comm_res = nullptr;
+    cudaStream_t s_route = nullptr, s_return = nullptr;
+    ShardSlot slots[DEPTH];
+    uint32_t next = 0;
+    int pending = -1;              // slot whose decide + return stages have not been issued yet
+    cudaEvent_t ev_tmp = nullptr;
+};
 
 // per-batch scratch; several sets so that the front halves of the next batches can overlap the back half of
 // the current one
@@ -106,6 +179,7 @@ struct gcra_engine {
     uint64_t ops_count = 0, cleanup_modulo = 0;
     uint64_t seen_allowed = 0, seen_expired_hits = 0;
     uint64_t n_sweeps = 0, n_grows = 0;
+    Shard *shard = nullptr;          // multi-GPU: native NCCL pipeline (gcra_shard_*)
     // ring
     std::vector<RingSlot> ring;
     uint32_t ring_cap = 0;
@@ -573,6 +647,17 @@ void gcra_destroy(gcra_engine *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    if (h->shard) {
+        Shard *sh = h->shard;
+        for (auto &sl : sh->slots) {
+            cudaFree(sl.routed); cudaFree(sl.recv_req); cudaFree(sl.recv_res); cudaFree(sl.back_res); cudaFree(sl.src_index);
+            cudaFree(sl.counts_dev); cudaFreeHost(sl.counts_host);
+            cudaEventDestroy(sl.ev_ready); cudaEventDestroy(sl.ev_counts); cudaEventDestroy(sl.ev_routed); cudaEventDestroy(sl.ev_done);
+        }
+        if (nccl_rt::g_api.CommDestroy) { nccl_rt::g_api.CommDestroy(sh->comm_counts); nccl_rt::g_api.CommDestroy(sh->comm_req); nccl_rt::g_api.CommDestroy(sh->comm_res); }
+        cudaStreamDestroy(sh->s_route); cudaStreamDestroy(sh->s_return); cudaEventDestroy(sh->ev_tmp);
+        delete sh;
+    }
     for (auto &s : h->ring) {
         cudaFreeHost(s.h_req); cudaFreeHost(s.h_res); cudaFree(s.d_req); cudaFree(s.d_res);
         cudaEventDestroy(s.ev_in); cudaEventDestroy(s.ev_comp); cudaEventDestroy(s.ev_done);
@@ -1001,6 +1086,168 @@ int32_t gcra_snapshot_load(gcra_engine *h, const char *path) {
     h->seen_allowed = hd.counters[C_ALLOWED];
     h->seen_expired_hits = hd.counters[C_EXPIRED_HITS];
     for (int i = 0; i < gcra_engine::N_SNAP; i++) h->snap_used[i] = false;
+    return GCRA_OK;
+}
+
+
+// ---- multi-GPU: the whole sharded tick in native code (one call per tick) ------------------------------
+#define NK(call)                                                                              \
+    do {                                                                                      \
+        int r_ = (call);                                                                      \
+        if (r_ != 0) {                                                                        \
+            h->err = std::string(#call) + ": " + (nccl_rt::g_api.GetErrorString ? nccl_rt::g_api.GetErrorString(r_) : "nccl error"); \
+            return GCRA_INTERNAL;                                                             \
+        }                                                                                     \
+    } while (0)
+
+int32_t gcra_shard_unique_ids(void *out_3x128) {
+    if (!nccl_rt::load()) return GCRA_INTERNAL;
+    for (int i = 0; i < 3; i++)
+        if (nccl_rt::g_api.GetUniqueId((nccl_rt::UniqueId *)((char *)out_3x128 + 128 * i)) != 0) return GCRA_INTERNAL;
+    return GCRA_OK;
+}
+
+int32_t gcra_shard_init(gcra_engine *h, int32_t rank, int32_t world, const void *ids_3x128, uint32_t max_rows) {
+    CK(cudaSetDevice(h->device));
+    if (h->shard) { h->err = "shard already initialised"; return GCRA_INTERNAL; }
+    if (world < 1 || world > ROUTE_MAX_SHARDS || rank < 0 || rank >= world) { h->err = "bad rank / world"; return GCRA_INTERNAL; }
+    if (max_rows == 0 || max_rows > h->max_batch) { h->err = "max_rows must be in 1..max_batch"; return GCRA_INTERNAL; }
+    if (!nccl_rt::load()) { h->err = "libnccl.so.2 not found"; return GCRA_INTERNAL; }
+    Shard *sh = new Shard();
+    sh->rank = rank; sh->world = world; sh->max_rows = max_rows;
+    const nccl_rt::UniqueId *ids = (const nccl_rt::UniqueId *)ids_3x128;
+    // one communicator per stage: NCCL runs the operations of ONE communicator in issue order
+    NK(nccl_rt::g_api.CommInitRank(&sh->comm_counts, world, ids[0], rank));
+    NK(nccl_rt::g_api.CommInitRank(&sh->comm_req, world, ids[1], rank));
+    NK(nccl_rt::g_api.CommInitRank(&sh->comm_res, world, ids[2], rank));
+    CK(cudaStreamCreateWithFlags(&sh->s_route, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&sh->s_return, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&sh->ev_tmp, cudaEventDisableTiming));
+    for (auto &sl : sh->slots) {
+        CK(cudaMalloc(&sl.routed, (size_t)max_rows * sizeof(gcra_request)));
+        CK(cudaMalloc(&sl.recv_req, (size_t)max_rows * sizeof(gcra_request)));
+        CK(cudaMalloc(&sl.recv_res, (size_t)max_rows * sizeof(gcra_result)));
+        CK(cudaMalloc(&sl.back_res, (size_t)max_rows * sizeof(gcra_result)));
+        CK(cudaMalloc(&sl.src_index, (size_t)max_rows * sizeof(u32)));
+        CK(cudaMalloc(&sl.counts_dev, 2 * ROUTE_MAX_SHARDS * sizeof(u32)));
+        CK(cudaMallocHost(&sl.counts_host, 2 * ROUTE_MAX_SHARDS * sizeof(u32)));
+        CK(cudaEventCreateWithFlags(&sl.ev_ready, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&sl.ev_counts, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&sl.ev_routed, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+        sl.send.resize(world); sl.recv.resize(world); sl.send_off.resize(world); sl.recv_off.resize(world);
+    }
+    h->shard = sh;
+    return GCRA_OK;
+}
+
+// stages 3+4 of a tick: the engine's kernels (pipelined inside the engine) and the way back
+static int shard_issue_decide_return(gcra_engine *h) {
+    Shard *sh = h->shard;
+    if (sh->pending < 0) return GCRA_OK;
+    ShardSlot &sl = sh->slots[sh->pending];
+    sh->pending = -1;
+    const int W = sh->world;
+    cudaEvent_t done = nullptr;
+    RC(launch_pipelined(h, sl.n_recv, sl.recv_req, false, 0, sl.recv_res, sl.ev_routed, &done));
+    if (done) CK(cudaStreamWaitEvent(sh->s_return, done, 0));
+    else CK(cudaStreamWaitEvent(sh->s_return, sl.ev_routed, 0));
+    NK(nccl_rt::g_api.GroupStart());
+    for (int p = 0; p < W; p++) {
+        // results of the rows peer p sent me go back to p; my own rows' results arrive in partition order
+        NK(nccl_rt::g_api.Send(sl.recv_res + sl.recv_off[p], sl.recv[p] * sizeof(gcra_result), nccl_rt::kUint8, p, sh->comm_res, sh->s_return));
+        NK(nccl_rt::g_api.Recv(sl.back_res + sl.send_off[p], sl.send[p] * sizeof(gcra_result), nccl_rt::kUint8, p, sh->comm_res, sh->s_return));
+    }
+    NK(nccl_rt::g_api.GroupEnd());
+    if (sl.n) {
+        route_unpermute_kernel<<<(sl.n + TILE_THREADS - 1) / TILE_THREADS, TILE_THREADS, 0, sh->s_return>>>(
+            sl.back_res, sl.src_index, sl.n, sl.d_res_user);
+        h->launches++;
+    }
+    CK(cudaEventRecord(sl.ev_done, sh->s_return));
+    CK(cudaGetLastError());
+    return GCRA_OK;
+}
+
+int32_t gcra_shard_submit(gcra_engine *h, uint64_t n64, const gcra_request *d_req, gcra_result *d_res, void *ready_stream) {
+    CK(cudaSetDevice(h->device));
+    Shard *sh = h->shard;
+    if (!sh) { h->err = "gcra_shard_init first"; return GCRA_INTERNAL; }
+    if (n64 > sh->max_rows) { h->err = "tick larger than max_rows"; return GCRA_INTERNAL; }
+    const uint32_t n = (uint32_t)n64;
+    const int W = sh->world;
+    const int k = (int)(sh->next++ % Shard::DEPTH);
+    ShardSlot &sl = sh->slots[k];
+    if ((int)sh->pending == k) RC(shard_issue_decide_return(h));
+    if (sl.used) CK(cudaStreamWaitEvent(sh->s_route, sl.ev_done, 0));     // the slot's buffers are free again
+    sl.used = true; sl.n = n; sl.d_res_user = d_res;
+    if (ready_stream) {
+        CK(cudaEventRecord(sl.ev_ready, (cudaStream_t)ready_stream));
+        CK(cudaStreamWaitEvent(sh->s_route, sl.ev_ready, 0));
+    }
+    // stage 1: stable partition by owner + count exchange
+    if (n) {
+        uint32_t tiles = (n + TILE_THREADS - 1) / TILE_THREADS;
+        route_count_kernel<<<tiles, TILE_THREADS, 0, sh->s_route>>>(d_req, n, (u32)W, tiles, h->route_counts);
+        route_scan_kernel<<<1, TILE_THREADS, 0, sh->s_route>>>(h->route_counts, (u32)W, tiles, sl.counts_dev);
+        route_scatter_kernel<<<tiles, TILE_THREADS, 0, sh->s_route>>>(d_req, n, (u32)W, tiles, h->route_counts, sl.routed, sl.src_index);
+        h->launches += 3;
+    } else {
+        CK(cudaMemsetAsync(sl.counts_dev, 0, W * sizeof(u32), sh->s_route));
+    }
+    NK(nccl_rt::g_api.GroupStart());
+    for (int p = 0; p < W; p++) {
+        NK(nccl_rt::g_api.Send(sl.counts_dev + p, 1, nccl_rt::kUint32, p, sh->comm_counts, sh->s_route));
+        NK(nccl_rt::g_api.Recv(sl.counts_dev + W + p, 1, nccl_rt::kUint32, p, sh->comm_counts, sh->s_route));
+    }
+    NK(nccl_rt::g_api.GroupEnd());
+    CK(cudaMemcpyAsync(sl.counts_host, sl.counts_dev, 2 * W * sizeof(u32), cudaMemcpyDeviceToHost, sh->s_route));
+    CK(cudaEventRecord(sl.ev_counts, sh->s_route));
+    // while this runs, enqueue the previous tick's engine kernels and its way back
+    RC(shard_issue_decide_return(h));
+    // stage 2: request all-to-all (the counts are the only thing the host waits for)
+    CK(cudaEventSynchronize(sl.ev_counts));
+    size_t so = 0, ro = 0;
+    for (int p = 0; p < W; p++) {
+        sl.send[p] = sl.counts_host[p]; sl.recv[p] = sl.counts_host[W + p];
+        sl.send_off[p] = so; sl.recv_off[p] = ro;
+        so += sl.send[p]; ro += sl.recv[p];
+    }
+    if (ro > sh->max_rows) { h->err = "shard received more rows than max_rows"; return GCRA_INTERNAL; }
+    sl.n_recv = (uint32_t)ro;
+    NK(nccl_rt::g_api.GroupStart());
+    for (int p = 0; p < W; p++) {
+        NK(nccl_rt::g_api.Send(sl.routed + sl.send_off[p], sl.send[p] * sizeof(gcra_request), nccl_rt::kUint8, p, sh->comm_req, sh->s_route));
+        NK(nccl_rt::g_api.Recv(sl.recv_req + sl.recv_off[p], sl.recv[p] * sizeof(gcra_request), nccl_rt::kUint8, p, sh->comm_req, sh->s_route));
+    }
+    NK(nccl_rt::g_api.GroupEnd());
+    CK(cudaEventRecord(sl.ev_routed, sh->s_route));
+    CK(cudaGetLastError());
+    sh->pending = k;
+    return GCRA_OK;
+}
+
+// make `stream` wait for the results of the tick submitted `ticks_back` submissions ago (0 = the latest);
+// only the last DEPTH-1 ticks can be addressed
+int32_t gcra_shard_wait_tick(gcra_engine *h, uint32_t ticks_back, void *stream) {
+    CK(cudaSetDevice(h->device));
+    Shard *sh = h->shard;
+    if (!sh || ticks_back >= (uint32_t)Shard::DEPTH - 1 || ticks_back >= sh->next) { h->err = "bad tick"; return GCRA_INTERNAL; }
+    const int k = (int)((sh->next - 1 - ticks_back) % Shard::DEPTH);
+    if (sh->pending == k) RC(shard_issue_decide_return(h));
+    if (stream) CK(cudaStreamWaitEvent((cudaStream_t)stream, sh->slots[k].ev_done, 0));
+    else CK(cudaEventSynchronize(sh->slots[k].ev_done));
+    return GCRA_OK;
+}
+
+int32_t gcra_shard_join(gcra_engine *h, void *stream) {
+    CK(cudaSetDevice(h->device));
+    Shard *sh = h->shard;
+    if (!sh) { h->err = "gcra_shard_init first"; return GCRA_INTERNAL; }
+    RC(shard_issue_decide_return(h));
+    CK(cudaEventRecord(sh->ev_tmp, sh->s_return));
+    if (stream) CK(cudaStreamWaitEvent((cudaStream_t)stream, sh->ev_tmp, 0));
+    else CK(cudaEventSynchronize(sh->ev_tmp));
     return GCRA_OK;
 }
 

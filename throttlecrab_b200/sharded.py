@@ -191,3 +191,45 @@ class ShardedLimiter:
         n_recv = self.submit(d_req, d_res)
         self.finish()
         return n_recv
+
+
+class NativeShardedLimiter:
+    """The same pipeline driven by ONE C call per tick (gcra_shard_submit): partition, NCCL count exchange and
+    all-to-alls (libnccl resolved with dlopen inside the library), the engine's pipelined kernels and the way
+    back all live in libgcra_b200.so.  torch.distributed is used once, to hand the three ncclUniqueIds that
+    rank 0 creates to the other ranks."""
+
+    def __init__(self, limiter, dist, device, max_rows=None):
+        import ctypes as C
+        self.lim, self.dist, self.dev = limiter, dist, device
+        self.L, self.h = limiter._L, limiter._h
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.max_rows = max_rows or limiter.store.max_batch
+        ids = torch.zeros(384, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (C.c_char * 384)()
+            if self.L.gcra_shard_unique_ids(C.addressof(buf)) != 0:
+                raise RuntimeError("ncclGetUniqueId failed (libnccl.so.2 not loadable)")
+            ids = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        ids = ids.to(device)
+        dist.broadcast(ids, src=0)
+        raw = bytes(ids.cpu().numpy().tobytes())
+        limiter.store._check(self.L.gcra_shard_init(self.h, self.rank, self.world, raw, self.max_rows))
+        self.n_submitted = 0
+
+    def submit(self, d_req, d_res, ready_stream=None):
+        n = d_req.numel() // REQ_B
+        st = ready_stream if ready_stream is not None else torch.cuda.current_stream(self.dev).cuda_stream
+        self.lim.store._check(self.L.gcra_shard_submit(self.h, n, d_req.data_ptr(), d_res.data_ptr(), st))
+        self.n_submitted += 1
+
+    def wait_tick(self, ticks_back, stream):
+        """make `stream` (a torch stream) wait for the results of an earlier tick (0 = latest)"""
+        self.lim.store._check(self.L.gcra_shard_wait_tick(self.h, ticks_back, stream.cuda_stream))
+
+    def finish(self):
+        self.lim.store._check(self.L.gcra_shard_join(self.h, torch.cuda.current_stream(self.dev).cuda_stream))
+
+    def step(self, d_req, d_res):
+        self.submit(d_req, d_res)
+        self.finish()
