@@ -112,7 +112,7 @@ struct Shard {
     int rank = 0, world = 0;
     uint32_t max_rows = 0;
     nccl_rt::Comm comm_counts = nullptr, comm_req = nullptr, comm_res = nullptr;
-    cudaStream_t s_route = nullptr, s_return = nullptr;
+    cudaStream_t s_part = nullptr, s_route = nullptr, s_return = nullptr;   // partition+counts | request all-to-all | way back
     ShardSlot slots[DEPTH];
     uint32_t next = 0;
     int pending = -1;              // slot whose decide + return stages have not been issued yet
@@ -655,7 +655,7 @@ void gcra_destroy(gcra_engine *h) {
             cudaEventDestroy(sl.ev_ready); cudaEventDestroy(sl.ev_counts); cudaEventDestroy(sl.ev_routed); cudaEventDestroy(sl.ev_done);
         }
         if (nccl_rt::g_api.CommDestroy) { nccl_rt::g_api.CommDestroy(sh->comm_counts); nccl_rt::g_api.CommDestroy(sh->comm_req); nccl_rt::g_api.CommDestroy(sh->comm_res); }
-        cudaStreamDestroy(sh->s_route); cudaStreamDestroy(sh->s_return); cudaEventDestroy(sh->ev_tmp);
+        cudaStreamDestroy(sh->s_part); cudaStreamDestroy(sh->s_route); cudaStreamDestroy(sh->s_return); cudaEventDestroy(sh->ev_tmp);
         delete sh;
     }
     for (auto &s : h->ring) {
@@ -1120,6 +1120,7 @@ int32_t gcra_shard_init(gcra_engine *h, int32_t rank, int32_t world, const void 
     NK(nccl_rt::g_api.CommInitRank(&sh->comm_counts, world, ids[0], rank));
     NK(nccl_rt::g_api.CommInitRank(&sh->comm_req, world, ids[1], rank));
     NK(nccl_rt::g_api.CommInitRank(&sh->comm_res, world, ids[2], rank));
+    CK(cudaStreamCreateWithFlags(&sh->s_part, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&sh->s_route, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&sh->s_return, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&sh->ev_tmp, cudaEventDisableTiming));
@@ -1179,34 +1180,36 @@ int32_t gcra_shard_submit(gcra_engine *h, uint64_t n64, const gcra_request *d_re
     const int k = (int)(sh->next++ % Shard::DEPTH);
     ShardSlot &sl = sh->slots[k];
     if ((int)sh->pending == k) RC(shard_issue_decide_return(h));
-    if (sl.used) CK(cudaStreamWaitEvent(sh->s_route, sl.ev_done, 0));     // the slot's buffers are free again
+    if (sl.used) CK(cudaStreamWaitEvent(sh->s_part, sl.ev_done, 0));     // the slot's buffers are free again
     sl.used = true; sl.n = n; sl.d_res_user = d_res;
     if (ready_stream) {
         CK(cudaEventRecord(sl.ev_ready, (cudaStream_t)ready_stream));
-        CK(cudaStreamWaitEvent(sh->s_route, sl.ev_ready, 0));
+        CK(cudaStreamWaitEvent(sh->s_part, sl.ev_ready, 0));
     }
     // stage 1: stable partition by owner + count exchange
     if (n) {
         uint32_t tiles = (n + TILE_THREADS - 1) / TILE_THREADS;
-        route_count_kernel<<<tiles, TILE_THREADS, 0, sh->s_route>>>(d_req, n, (u32)W, tiles, h->route_counts);
-        route_scan_kernel<<<1, TILE_THREADS, 0, sh->s_route>>>(h->route_counts, (u32)W, tiles, sl.counts_dev);
-        route_scatter_kernel<<<tiles, TILE_THREADS, 0, sh->s_route>>>(d_req, n, (u32)W, tiles, h->route_counts, sl.routed, sl.src_index);
+        route_count_kernel<<<tiles, TILE_THREADS, 0, sh->s_part>>>(d_req, n, (u32)W, tiles, h->route_counts);
+        route_scan_kernel<<<1, TILE_THREADS, 0, sh->s_part>>>(h->route_counts, (u32)W, tiles, sl.counts_dev);
+        route_scatter_kernel<<<tiles, TILE_THREADS, 0, sh->s_part>>>(d_req, n, (u32)W, tiles, h->route_counts, sl.routed, sl.src_index);
         h->launches += 3;
     } else {
-        CK(cudaMemsetAsync(sl.counts_dev, 0, W * sizeof(u32), sh->s_route));
+        CK(cudaMemsetAsync(sl.counts_dev, 0, W * sizeof(u32), sh->s_part));
     }
     NK(nccl_rt::g_api.GroupStart());
     for (int p = 0; p < W; p++) {
-        NK(nccl_rt::g_api.Send(sl.counts_dev + p, 1, nccl_rt::kUint32, p, sh->comm_counts, sh->s_route));
-        NK(nccl_rt::g_api.Recv(sl.counts_dev + W + p, 1, nccl_rt::kUint32, p, sh->comm_counts, sh->s_route));
+        NK(nccl_rt::g_api.Send(sl.counts_dev + p, 1, nccl_rt::kUint32, p, sh->comm_counts, sh->s_part));
+        NK(nccl_rt::g_api.Recv(sl.counts_dev + W + p, 1, nccl_rt::kUint32, p, sh->comm_counts, sh->s_part));
     }
     NK(nccl_rt::g_api.GroupEnd());
-    CK(cudaMemcpyAsync(sl.counts_host, sl.counts_dev, 2 * W * sizeof(u32), cudaMemcpyDeviceToHost, sh->s_route));
-    CK(cudaEventRecord(sl.ev_counts, sh->s_route));
+    CK(cudaMemcpyAsync(sl.counts_host, sl.counts_dev, 2 * W * sizeof(u32), cudaMemcpyDeviceToHost, sh->s_part));
+    CK(cudaEventRecord(sl.ev_counts, sh->s_part));
     // while this runs, enqueue the previous tick's engine kernels and its way back
     RC(shard_issue_decide_return(h));
-    // stage 2: request all-to-all (the counts are the only thing the host waits for)
+    // stage 2: request all-to-all on its own stream (the partition + count exchange of the NEXT tick overlap
+    // it); the counts are the only thing the host waits for
     CK(cudaEventSynchronize(sl.ev_counts));
+    CK(cudaStreamWaitEvent(sh->s_route, sl.ev_counts, 0));
     size_t so = 0, ro = 0;
     for (int p = 0; p < W; p++) {
         sl.send[p] = sl.counts_host[p]; sl.recv[p] = sl.counts_host[W + p];
