@@ -516,9 +516,23 @@ static int launch_batch(gcra_engine *h, uint32_t n, const void *d_req, bool comp
     // order after every earlier batch (they may have been submitted pipelined on the engine's streams),
     // which also frees this scratch set
     for (auto &o : h->scr) if (o.back_recorded) CK(cudaStreamWaitEvent(st, o.ev_back, 0));
-    u64 *sorted = nullptr;
-    RC(enqueue_front(h, sc, n, d_req, compact, now_batch, d_res, st, timed, &sorted));
-    RC(enqueue_back(h, sc, n, sorted, d_res, st, timed));
+    static const bool no_small = getenv("GCRA_NO_SMALL") && atoi(getenv("GCRA_NO_SMALL"));   // A/B switch for tools/latency_probe.py
+    if (n <= SMALL_MAX && !no_small) {
+        // small batch (a single rate_limit call, a lightly loaded actor): one CTA does ingest, ordering and
+        // the compare-and-update in a single launch
+        if (timed) { CK(cudaEventRecord(h->ev[0], st)); CK(cudaEventRecord(h->ev[1], st)); CK(cudaEventRecord(h->ev[2], st)); }
+        if (compact)
+            small_batch_kernel<true><<<1, TILE_THREADS, 0, st>>>(h->tab, d_req, h->d_pol, h->npol, now_batch, n, sc.drec, d_res);
+        else
+            small_batch_kernel<false><<<1, TILE_THREADS, 0, st>>>(h->tab, d_req, nullptr, 0, 0, n, sc.drec, d_res);
+        h->launches++;
+        if (timed) { CK(cudaEventRecord(h->ev[3], st)); h->ev_valid = true; }
+        CK(cudaGetLastError());
+    } else {
+        u64 *sorted = nullptr;
+        RC(enqueue_front(h, sc, n, d_req, compact, now_batch, d_res, st, timed, &sorted));
+        RC(enqueue_back(h, sc, n, sorted, d_res, st, timed));
+    }
     CK(cudaEventRecord(sc.ev_back, st));
     sc.back_recorded = true;
     return snapshot_async(h, n, st);

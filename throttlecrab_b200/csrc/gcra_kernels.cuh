@@ -71,6 +71,68 @@ __device__ __forceinline__ void write_result(gcra_result *out, i64 remaining, i6
     reinterpret_cast<longlong2 *>(out)[1] = b;
 }
 
+// validation (rate_limiter.rs:111-117), parameter derivation, key probe/claim for ONE request whose record
+// sits at `rec` (shared or global memory).  Writes the derived request, the error result if any, and returns
+// the sort key (slot << 32 | i).  Must be called by all 32 lanes of a warp (warp-aggregated counters).
+template <bool COMPACT>
+__device__ __forceinline__ u64 ingest_one(const Table &t, const unsigned char *rec, bool in_range,
+                                          const PolicyDerived *__restrict__ pol, u32 npol, i64 now_batch, u32 i,
+                                          Req *__restrict__ drec, gcra_result *__restrict__ out) {
+    int status = 0;
+    u64 key_hash = 0;
+    Req r = {0, 0, 0, 0};
+    if (in_range) {
+        if (COMPACT) {
+            ulonglong2 w = *reinterpret_cast<const ulonglong2 *>(rec);
+            key_hash = w.x;
+            int qty = (int)(u32)(w.y & 0xffffffffULL);
+            u32 p = (u32)(w.y >> 32);
+            r.q = qty;
+            r.now = now_batch;
+            if (qty < 0) status = GCRA_NEGATIVE_QUANTITY;          // rate_limiter.rs:111-113
+            else if (p >= npol) status = GCRA_INTERNAL;
+            else {
+                PolicyDerived pd = pol[p];
+                status = pd.status;
+                r.ei = pd.ei;
+                r.dvt = pd.dvt;
+            }
+        } else {
+            const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(rec);
+            ulonglong2 w0 = q[0], w1 = q[1], w2 = q[2];
+            key_hash = w0.x;
+            i64 max_burst = (i64)w0.y, count = (i64)w1.x, period = (i64)w1.y;
+            r.q = (i64)w2.x;
+            r.now = (i64)w2.y;
+            if (r.q < 0) status = GCRA_NEGATIVE_QUANTITY;          // :111-113
+            else if (max_burst <= 0 || count <= 0 || period <= 0) status = GCRA_INVALID_RATE_LIMIT;  // :115-117
+            else status = derive_params(max_burst, count, period, &r.ei, &r.dvt);
+        }
+        // a pre-epoch `now` makes the reference read the wall clock (:128-143): not reproducible
+        if (status == 0 && r.now < 0) status = GCRA_INTERNAL;
+    }
+    u32 slot = t.null_slot;
+    bool fresh = false;
+    if (in_range && status == 0) {
+        slot = find_or_claim(t, stored_key(key_hash), fresh);
+        if (slot == t.null_slot) status = GCRA_INTERNAL;   // table full
+        else if (fresh) t.state[slot].off = (u64)EXP_PHANTOM;
+    }
+    if (in_range) {
+        reinterpret_cast<longlong2 *>(drec + i)[0] = make_longlong2(r.now, r.ei);
+        reinterpret_cast<longlong2 *>(drec + i)[1] = make_longlong2(r.dvt, r.q);
+        if (status != 0) write_result(out + i, 0, 0, 0, status, 0);
+    }
+    // warp-aggregated counters
+    u32 mf = __ballot_sync(0xffffffffu, fresh);
+    u32 me = __ballot_sync(0xffffffffu, in_range && status != 0);
+    if ((threadIdx.x & 31) == 0) {
+        if (mf) atomicAdd(&t.counters[C_OCCUPIED], (u64)__popc(mf));
+        if (me) atomicAdd(&t.counters[C_ERRORS], (u64)__popc(me));
+    }
+    return ((u64)slot << 32) | i;
+}
+
 template <bool COMPACT>
 __global__ void __launch_bounds__(TILE_THREADS)
 ingest_kernel(Table t, const void *__restrict__ req_base, const PolicyDerived *__restrict__ pol,
@@ -95,62 +157,8 @@ ingest_kernel(Table t, const void *__restrict__ req_base, const PolicyDerived *_
 
     const u32 i = base + threadIdx.x;
     const bool in_range = threadIdx.x < cnt;
-    int status = 0;
-    u64 key_hash = 0;
-    Req r = {0, 0, 0, 0};
-    if (in_range) {
-        if (COMPACT) {
-            const gcra_request16 *q = reinterpret_cast<const gcra_request16 *>(stage) + threadIdx.x;
-            ulonglong2 w = *reinterpret_cast<const ulonglong2 *>(q);
-            key_hash = w.x;
-            int qty = (int)(u32)(w.y & 0xffffffffULL);
-            u32 p = (u32)(w.y >> 32);
-            r.q = qty;
-            r.now = now_batch;
-            if (qty < 0) status = GCRA_NEGATIVE_QUANTITY;          // rate_limiter.rs:111-113
-            else if (p >= npol) status = GCRA_INTERNAL;
-            else {
-                PolicyDerived pd = pol[p];
-                status = pd.status;
-                r.ei = pd.ei;
-                r.dvt = pd.dvt;
-            }
-        } else {
-            const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(
-                reinterpret_cast<const gcra_request *>(stage) + threadIdx.x);
-            ulonglong2 w0 = q[0], w1 = q[1], w2 = q[2];
-            key_hash = w0.x;
-            i64 max_burst = (i64)w0.y, count = (i64)w1.x, period = (i64)w1.y;
-            r.q = (i64)w2.x;
-            r.now = (i64)w2.y;
-            if (r.q < 0) status = GCRA_NEGATIVE_QUANTITY;          // :111-113
-            else if (max_burst <= 0 || count <= 0 || period <= 0) status = GCRA_INVALID_RATE_LIMIT;  // :115-117
-            else status = derive_params(max_burst, count, period, &r.ei, &r.dvt);
-        }
-        // a pre-epoch `now` makes the reference read the wall clock (:128-143): not reproducible
-        if (status == 0 && r.now < 0) status = GCRA_INTERNAL;
-    }
-
-    u32 slot = t.null_slot;
-    bool fresh = false;
-    if (in_range && status == 0) {
-        slot = find_or_claim(t, stored_key(key_hash), fresh);
-        if (slot == t.null_slot) status = GCRA_INTERNAL;   // table full
-        else if (fresh) t.state[slot].off = (u64)EXP_PHANTOM;
-    }
-    if (in_range) {
-        reinterpret_cast<longlong2 *>(drec + i)[0] = make_longlong2(r.now, r.ei);
-        reinterpret_cast<longlong2 *>(drec + i)[1] = make_longlong2(r.dvt, r.q);
-        sortkeys[i] = ((u64)slot << 32) | i;
-        if (status != 0) write_result(out + i, 0, 0, 0, status, 0);
-    }
-    // warp-aggregated counters
-    u32 mf = __ballot_sync(0xffffffffu, fresh);
-    u32 me = __ballot_sync(0xffffffffu, in_range && status != 0);
-    if ((threadIdx.x & 31) == 0) {
-        if (mf) atomicAdd(&t.counters[C_OCCUPIED], (u64)__popc(mf));
-        if (me) atomicAdd(&t.counters[C_ERRORS], (u64)__popc(me));
-    }
+    const u64 key = ingest_one<COMPACT>(t, stage + (size_t)threadIdx.x * RSZ, in_range, pol, npol, now_batch, i, drec, out);
+    if (in_range) sortkeys[i] = key;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -389,12 +397,11 @@ __device__ __forceinline__ void store_state(const Table &t, u32 slot, const RunS
 #endif
 constexpr int DECIDE_THREADS = GCRA_DECIDE_THREADS;   // warps are independent: the CTA size only sets scheduling granularity
 
-__global__ void __launch_bounds__(DECIDE_THREADS, 1024 / DECIDE_THREADS)
-decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ drec, u32 n,
-              gcra_result *__restrict__ out, LongRun *__restrict__ long_runs, LongRun *__restrict__ giant_runs,
-              u32 *__restrict__ long_count) {
-    const u32 lane = threadIdx.x & 31;
-    const u32 warp_global = (blockIdx.x * DECIDE_THREADS + threadIdx.x) >> 5;
+// one warp, one chunk of 32 sorted positions (see the comment above run_chunk)
+__device__ __forceinline__ void decide_chunk(const Table &t, const u64 *sorted, const Req *__restrict__ drec, u32 n,
+                                             gcra_result *__restrict__ out, LongRun *__restrict__ long_runs,
+                                             LongRun *__restrict__ giant_runs, u32 *__restrict__ long_count,
+                                             u32 warp_global, u32 lane) {
     const u32 base = warp_global * 32;
     if (base >= n) return;   // whole warp
 
@@ -548,6 +555,48 @@ decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ d
         if (real_inc) atomicAdd(&t.counters[C_REAL], (u64)real_inc);
         if (exp_hits) atomicAdd(&t.counters[C_EXPIRED_HITS], (u64)exp_hits);
     }
+}
+
+__global__ void __launch_bounds__(DECIDE_THREADS, 1024 / DECIDE_THREADS)
+decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ drec, u32 n,
+              gcra_result *__restrict__ out, LongRun *__restrict__ long_runs, LongRun *__restrict__ giant_runs,
+              u32 *__restrict__ long_count) {
+    decide_chunk(t, sorted, drec, n, out, long_runs, giant_runs, long_count,
+                 (blockIdx.x * DECIDE_THREADS + threadIdx.x) >> 5, threadIdx.x & 31);
+}
+
+// Small batches (n < LONG_RUN_MIN, e.g. one RateLimiter::rate_limit call or a lightly loaded actor): ONE CTA
+// does everything -- ingest, a bitonic sort of the (slot, index) keys in shared memory, and the warp-chunk
+// compare-and-update -- instead of 13 launches.  No run can reach LONG_RUN_MIN, so no work list is produced.
+constexpr u32 SMALL_MAX = 255;
+static_assert(SMALL_MAX < GCRA_LONG_MIN && SMALL_MAX < TILE_THREADS, "small path must not create long runs");
+
+template <bool COMPACT>
+__global__ void __launch_bounds__(TILE_THREADS)
+small_batch_kernel(Table t, const void *__restrict__ req_base, const PolicyDerived *__restrict__ pol, u32 npol,
+                   i64 now_batch, u32 n, Req *__restrict__ drec, gcra_result *__restrict__ out) {
+    constexpr u32 RSZ = COMPACT ? sizeof(gcra_request16) : sizeof(gcra_request);
+    __shared__ u64 keys[TILE_THREADS];
+    const u32 tid = threadIdx.x;
+    const bool in_range = tid < n;
+    const u64 key = ingest_one<COMPACT>(t, (const unsigned char *)req_base + (size_t)(in_range ? tid : 0) * RSZ, in_range,
+                                        pol, npol, now_batch, tid, drec, out);
+    keys[tid] = in_range ? key : ~0ULL;
+    __syncthreads();
+    // bitonic sort of 256 keys; (slot << 32 | index) is a total order, so equal slots stay in index order
+    for (u32 k = 2; k <= TILE_THREADS; k <<= 1) {
+        for (u32 j = k >> 1; j > 0; j >>= 1) {
+            const u32 partner = tid ^ j;
+            if (partner > tid) {
+                const u64 a = keys[tid], b = keys[partner];
+                const bool up = (tid & k) == 0;
+                if ((a > b) == up) { keys[tid] = b; keys[partner] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    __threadfence_block();   // drec / state written above are read below by other warps of this CTA
+    decide_chunk(t, keys, drec, n, out, nullptr, nullptr, nullptr, tid >> 5, tid & 31);
 }
 
 // ---------------------------------------------------------------------------------------------
