@@ -65,3 +65,21 @@ def test_engine_fails_loudly_without_a_gpu():
         pytest.skip("a GPU is present")
     with pytest.raises(RuntimeError):
         tc.AdaptiveStore(capacity=10)
+
+
+def test_rate_mirror_matches_reference_tests():
+    """throttlecrab/src/core/rate/tests.rs:5-63"""
+    S = 10**9
+    assert tc.Rate.per_second(10).period() == 100_000_000
+    assert tc.Rate.per_second(1).period() == S
+    assert tc.Rate.per_minute(60).period() == S
+    assert tc.Rate.per_minute(1).period() == 60 * S
+    assert tc.Rate.per_hour(3600).period() == S
+    assert tc.Rate.per_hour(1).period() == 3600 * S
+    assert tc.Rate.per_day(86400).period() == S
+    assert tc.Rate.per_day(1).period() == 86400 * S
+    assert tc.Rate.from_count_and_period(10, 60).period() == 6 * S
+    assert tc.Rate.from_count_and_period(30, 60).period() == 2 * S
+    assert tc.Rate.from_count_and_period(0, 60).period() == (2**64 - 1) * S
+    assert tc.Rate.from_count_and_period(10, 0).period() == (2**64 - 1) * S
+    assert tc.Rate.new(250_000_000).period() == 250_000_000

@@ -23,7 +23,7 @@ from . import _native
 from ._native import (REQ_DTYPE, RES_DTYPE, REQ16_DTYPE, POLICY_DTYPE, OK, NEGATIVE_QUANTITY,
                       INVALID_RATE_LIMIT, INTERNAL)
 
-__all__ = ["RateLimiter", "RateLimitResult", "CellError", "NegativeQuantity", "InvalidRateLimit",
+__all__ = ["RateLimiter", "RateLimitResult", "Rate", "CellError", "NegativeQuantity", "InvalidRateLimit",
            "Internal", "AdaptiveStore", "PeriodicStore", "ProbabilisticStore", "ManualStore",
            "hash_key", "derive_params", "REQ_DTYPE", "RES_DTYPE", "REQ16_DTYPE", "POLICY_DTYPE"]
 
@@ -98,6 +98,50 @@ def derive_params(max_burst, count_per_period, period):
     ei, dvt = C.c_int64(), C.c_int64()
     st = _native.lib().gcra_derive_params(max_burst, count_per_period, period, C.byref(ei), C.byref(dvt))
     return st, ei.value, dvt.value
+
+
+class Rate:
+    """core/rate/mod.rs:35-38: an emission interval (integer nanoseconds here instead of a Duration)."""
+
+    def __init__(self, period_ns):
+        self._period = int(period_ns)
+
+    @classmethod
+    def new(cls, period_ns):                       # rate/mod.rs:56-58
+        return cls(period_ns)
+
+    @classmethod
+    def per_second(cls, n):                        # :74-78  Duration::from_secs(1) / n as u32
+        return cls(NS // _u32(n))
+
+    @classmethod
+    def per_minute(cls, n):                        # :94-98
+        return cls(60 * NS // _u32(n))
+
+    @classmethod
+    def per_hour(cls, n):                          # :114-118
+        return cls(3600 * NS // _u32(n))
+
+    @classmethod
+    def per_day(cls, n):                           # :134-138
+        return cls(86400 * NS // _u32(n))
+
+    @classmethod
+    def from_count_and_period(cls, count, period_seconds):   # :164-176
+        if count <= 0 or period_seconds <= 0:
+            return cls((2**64 - 1) * NS)           # Duration::from_secs(u64::MAX): "a very slow rate"
+        st, ei, _ = derive_params(1, count, period_seconds)
+        return cls(ei & (2**64 - 1))
+
+    def period(self):                              # :191-193
+        return self._period
+
+
+def _u32(n):
+    n = int(n) & 0xFFFFFFFF                        # `n as u32`; Duration / 0 panics in the reference
+    if n == 0:
+        raise ZeroDivisionError("divide by zero error when dividing duration by scalar")
+    return n
 
 
 class _GpuStore:
