@@ -737,6 +737,8 @@ int32_t gcra_derive_params(int64_t max_burst, int64_t count, int64_t period, int
 
 static int store_op(gcra_engine *h, int op, uint64_t key_hash, int64_t a, int64_t b, uint64_t ttl, int64_t now) {
     CK(cudaSetDevice(h->device));
+    // the table encodes 'no state' as a negative expiry: times before the epoch are outside its domain
+    if (op != 3 && now < 0) { h->err = "pre-epoch time is not supported"; return GCRA_INTERNAL; }
     if (op == 2) { int rc = ensure_room(h, 1); if (rc) return rc; }
     store_op_kernel<<<1, 1, 0, h->stream>>>(h->tab, op, stored_key(key_hash), a, b, ttl, now, h->d_op);
     h->launches++;
