@@ -88,13 +88,14 @@ typedef struct {
 
 typedef struct {
     uint64_t len;             /* entries holding state, like HashMap::len() (periodic.rs:113-116) */
-    uint64_t occupied_slots;  /* claimed table slots (len + keys seen only by denied requests) */
+    uint64_t occupied_slots;  /* slots whose key word is taken: len + keys without an entry (swept, or only ever denied) */
     uint64_t table_slots;
     uint64_t stash_entries;
     uint64_t allowed, denied, errors;   /* totals since creation */
     uint64_t expired_hits;    /* writes that replaced an expired entry (adaptive_cleanup.rs:233,267) */
     uint64_t sweeps, swept;   /* sweep launches / entries removed */
     uint64_t grows;
+    uint64_t purges;          /* passes that reclaimed the slots of keys without an entry */
 } gcra_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------- */

@@ -111,7 +111,7 @@ def test_full_size_sweep_round_trip(key_hash_of):
     assert removed == N_KEYS // 8 * 4 and st.len() == N_KEYS - removed
     assert st.sweep(traces.T0 + 6 * 10**9) == 0                    # idempotent
     assert st.sweep(traces.T0 + 10**12) == N_KEYS - removed and st.len() == 0
-    assert st.stats()["occupied_slots"] == 0
+    assert st.stats()["occupied_slots"] == N_KEYS      # swept keys keep their slots until a purge is needed
     again = np.empty(len(trace), tc.RES_DTYPE)
     for a in range(0, len(trace), TICK):
         lim.rate_limit_batch(ereq[a:a + TICK], out=again[a:a + TICK])

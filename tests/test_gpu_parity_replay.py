@@ -202,7 +202,8 @@ def test_tight_table_stash_and_growth(batch):
             swept += st_e.sweep(int(req["now_ns"][min(a + batch, n) - 1]))
     assert first_mismatch(res_o, res_e, req) is None, first_mismatch(res_o, res_e, req)
     s = st_e.stats()
-    assert s["grows"] >= (3 if batch == 64 else 2) and swept > 0
+    assert s["grows"] >= 1 and swept > 0
+    assert s["purges"] >= 1                       # swept keys' slots were reclaimed before growing again
     if batch == 64:
         assert s["stash_entries"] > 0             # keys really live in the stash
     assert s["table_slots"] < 4 * n_keys          # stayed tight: load well above the production 0.5

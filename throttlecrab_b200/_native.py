@@ -39,7 +39,7 @@ class Config(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in
                 ("len", "occupied_slots", "table_slots", "stash_entries", "allowed", "denied",
-                 "errors", "expired_hits", "sweeps", "swept", "grows")]
+                 "errors", "expired_hits", "sweeps", "swept", "grows", "purges")]
 
 
 def sources():

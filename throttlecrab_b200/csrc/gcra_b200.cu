@@ -178,7 +178,7 @@ struct gcra_engine {
     uint64_t last_removed = 0, last_total = 0;
     uint64_t ops_count = 0, cleanup_modulo = 0;
     uint64_t seen_allowed = 0, seen_expired_hits = 0;
-    uint64_t n_sweeps = 0, n_grows = 0;
+    uint64_t n_sweeps = 0, n_grows = 0, n_purges = 0;
     Shard *shard = nullptr;          // multi-GPU: native NCCL pipeline (gcra_shard_*)
     // ring
     std::vector<RingSlot> ring;
@@ -245,7 +245,7 @@ static int do_sweep(gcra_engine *h, int64_t now_ns, uint64_t *removed) {
     CK(cudaDeviceSynchronize());   // the sweep is exclusive: batches may be in flight on caller streams
     RC(refresh_counters(h, true));
     uint64_t before = h->h_counters[C_SWEPT];
-    uint32_t grid = (uint32_t)std::min<uint64_t>(((uint64_t)h->total_lines * 4 + TILE_THREADS * SWEEP_UNROLL - 1) / (TILE_THREADS * SWEEP_UNROLL), 148 * 16);
+    uint32_t grid = (uint32_t)std::min<uint64_t>(((uint64_t)h->total_lines * 2 + TILE_THREADS * SWEEP_UNROLL - 1) / (TILE_THREADS * SWEEP_UNROLL), 148 * 16);
     CK(cudaEventRecord(h->ev_sweep[0], h->stream));
     sweep_kernel<<<grid, TILE_THREADS, 0, h->stream>>>(h->tab, (u64)h->total_lines * 4, now_ns);
     CK(cudaEventRecord(h->ev_sweep[1], h->stream));
@@ -253,9 +253,25 @@ static int do_sweep(gcra_engine *h, int64_t now_ns, uint64_t *removed) {
     h->launches++;
     CK(cudaGetLastError());
     RC(refresh_counters(h, true));
+    h->occupied_ub = h->h_counters[C_OCCUPIED];
+    for (int i = 0; i < gcra_engine::N_SNAP; i++) h->snap_used[i] = false;
+    h->n_sweeps++;
+    if (removed) *removed = h->h_counters[C_SWEPT] - before;
+    return GCRA_OK;
+}
+
+// reclaim the slots of keys without an entry (exclusive); returns with fresh counters
+static int purge(gcra_engine *h) {
+    CK(cudaDeviceSynchronize());
+    const uint64_t slots = (uint64_t)h->total_lines * 4;
+    uint32_t grid = (uint32_t)std::min<uint64_t>((slots + TILE_THREADS - 1) / TILE_THREADS, 148 * 16);
+    purge_kernel<<<grid, TILE_THREADS, 0, h->stream>>>(h->tab, slots);
+    h->launches++;
+    CK(cudaGetLastError());
+    RC(refresh_counters(h, true));
     if (h->h_counters[C_STASH] == 0) {
         // no key lives in the stash any more: drop its tombstones
-        uint64_t first = (uint64_t)h->tab.nb_main * 4, cnt = (uint64_t)h->total_lines * 4 - first;
+        uint64_t first = (uint64_t)h->tab.nb_main * 4, cnt = slots - first;
         clear_slots_kernel<<<(uint32_t)((cnt + TILE_THREADS - 1) / TILE_THREADS), TILE_THREADS, 0, h->stream>>>(
             h->tab, first, cnt);
         h->launches++;
@@ -263,8 +279,7 @@ static int do_sweep(gcra_engine *h, int64_t now_ns, uint64_t *removed) {
     }
     h->occupied_ub = h->h_counters[C_OCCUPIED];
     for (int i = 0; i < gcra_engine::N_SNAP; i++) h->snap_used[i] = false;
-    h->n_sweeps++;
-    if (removed) *removed = h->h_counters[C_SWEPT] - before;
+    h->n_purges++;
     return GCRA_OK;
 }
 
@@ -327,6 +342,11 @@ static int ensure_room(gcra_engine *h, uint64_t n) {
     rc = refresh_counters(h, true);
     if (rc) return rc;
     h->occupied_ub = h->h_counters[C_OCCUPIED];
+    if (h->occupied_ub + n > load_limit(h) && h->h_counters[C_OCCUPIED] > h->h_counters[C_REAL]) {
+        // crowded: first give back the slots of keys that hold no entry (swept or only ever denied)
+        rc = purge(h);
+        if (rc) return rc;
+    }
     if (h->occupied_ub + n > load_limit(h)) {
         rc = grow(h, (h->occupied_ub + n));
         if (rc) return rc;
@@ -973,6 +993,7 @@ int32_t gcra_get_stats(gcra_engine *h, gcra_stats *out) {
     out->sweeps = h->n_sweeps;
     out->swept = c[C_SWEPT];
     out->grows = h->n_grows;
+    out->purges = h->n_purges;
     return GCRA_OK;
 }
 

@@ -14,8 +14,7 @@ typedef unsigned int u32;
 
 constexpr u64 KEY_EMPTY = 0;   // slot never used / swept
 constexpr u64 KEY_TOMB = 1;    // swept stash slot (stash probing continues past it)
-constexpr i64 EXP_EMPTY = -1;  // (tat=0, off=-1): no key in this slot
-constexpr i64 EXP_PHANTOM = -2;  // key claimed by a request that was denied: no state yet
+constexpr i64 EXP_EMPTY = -1;  // (tat=0, off=-1): the slot holds no state (free slot, or a key without an entry)
 constexpr i64 I64_MAX = 0x7fffffffffffffffLL;
 constexpr i64 I64_MIN = (-0x7fffffffffffffffLL - 1);
 
@@ -35,7 +34,7 @@ struct __align__(16) TatOff {
 };
 
 enum Counter {
-    C_OCCUPIED = 0,   // claimed slots (entries + phantoms)
+    C_OCCUPIED = 0,   // slots whose key word is taken (entries + keys without an entry)
     C_REAL,           // entries with state (HashMap::len)
     C_ALLOWED,
     C_DENIED,

@@ -116,7 +116,6 @@ __device__ __forceinline__ u64 ingest_one(const Table &t, const unsigned char *r
     if (in_range && status == 0) {
         slot = find_or_claim(t, stored_key(key_hash), fresh);
         if (slot == t.null_slot) status = GCRA_INTERNAL;   // table full
-        else if (fresh) t.state[slot].off = (u64)EXP_PHANTOM;
     }
     if (in_range) {
         reinterpret_cast<longlong2 *>(drec + i)[0] = make_longlong2(r.now, r.ei);
@@ -464,7 +463,7 @@ __device__ __forceinline__ void decide_chunk(const Table &t, const u64 *sorted, 
     if (head && mine) load_state(t, slot, s);
     s.tat = __shfl_sync(0xffffffffu, s.tat, hl);
     s.exp = __shfl_sync(0xffffffffu, s.exp, hl);
-    const bool was_phantom = s.exp == EXP_PHANTOM;   // same for every lane of the run
+    const bool was_phantom = s.exp < 0;              // the key has no entry yet (same for every lane of the run)
 
     Decision fin;
     bool changed = false;
@@ -683,7 +682,7 @@ decide_runs_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restric
         const u32 slot = (u32)(sorted[start] >> 32);
         RunState s0;
         load_state(t, slot, s0);
-        const bool was_phantom = s0.exp == EXP_PHANTOM;
+        const bool was_phantom = s0.exp < 0;           // the key has no entry yet
         Cands cd;
 #pragma unroll
         for (int c = 0; c < FSM_K; c++) { cd.tat[c] = s0.tat; cd.exp[c] = s0.exp; }
@@ -853,9 +852,12 @@ decide_runs_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restric
 // ---------------------------------------------------------------------------------------------
 // K2: sweep -- retain(expiry > now)
 // ---------------------------------------------------------------------------------------------
-// One thread per slot: a coalesced 128-bit load of the (tat, off) pair (the warp reads eight dense
-// 64-byte line halves per instruction, L1 bypass), expiry = tat + off, and only the slots whose
-// expiry <= now are touched again: pair reset to the empty pattern, key cleared.
+// One thread per slot: a coalesced 128-bit load of the (tat, off) pair (L1 bypass), expiry = tat + off, and
+// only the slots whose entry has expired are touched again: the pair is reset to the empty pattern with one
+// 128-bit store into the sector that was just read.  The KEY word is left in place (no scattered 8-byte
+// writes into sectors the sweep never reads): a key without an entry behaves exactly like an absent key
+// (Store::get sees nothing, the next allowed request creates the entry), it just keeps its slot -- which is
+// what a key that comes back wants anyway.  purge_kernel reclaims such slots when the table gets crowded.
 __device__ __forceinline__ ulonglong2 ld_stream(const void *p) {
     ulonglong2 v;
     asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
@@ -864,44 +866,65 @@ __device__ __forceinline__ ulonglong2 ld_stream(const void *p) {
 
 constexpr int SWEEP_UNROLL = 4;
 
+// One thread per 32-byte SECTOR of the state array (two slots): two 128-bit loads, and when either entry has
+// expired the whole sector is written back (two 128-bit stores), so DRAM only ever sees full-sector writes.
 __global__ void __launch_bounds__(TILE_THREADS)
 sweep_kernel(Table t, u64 total_slots, i64 now) {
-    u32 removed_real = 0, removed_all = 0, removed_stash = 0;
+    u32 removed = 0;
+    const u64 total_pairs = total_slots >> 1;            // the slot count is a power of two >= 64
     const u64 stride = (u64)gridDim.x * TILE_THREADS;
     u64 i = (u64)blockIdx.x * TILE_THREADS + threadIdx.x;
-    while (i < total_slots) {
-        ulonglong2 v[SWEEP_UNROLL];
+    while (i < total_pairs) {
+        ulonglong2 a[SWEEP_UNROLL], b[SWEEP_UNROLL];
 #pragma unroll
         for (int u = 0; u < SWEEP_UNROLL; u++) {
-            const u64 k = i + (u64)u * stride;
-            v[u] = make_ulonglong2(0, (u64)EXP_EMPTY);
-            if (k < total_slots) v[u] = ld_stream(&t.state[k]);
+            const u64 p = i + (u64)u * stride;
+            a[u] = make_ulonglong2(0, (u64)EXP_EMPTY);
+            b[u] = a[u];
+            if (p < total_pairs) { a[u] = ld_stream(&t.state[2 * p]); b[u] = ld_stream(&t.state[2 * p + 1]); }
         }
 #pragma unroll
         for (int u = 0; u < SWEEP_UNROLL; u++) {
-            const u64 k = i + (u64)u * stride;
-            const i64 ex = (i64)(v[u].x + v[u].y);
-            if (ex != EXP_EMPTY && ex <= now) {
-                const bool stash = k >= (u64)t.nb_main * 4;
-                *reinterpret_cast<longlong2 *>(&t.state[k]) = make_longlong2(0, EXP_EMPTY);
-                t.keys[k] = stash ? KEY_TOMB : KEY_EMPTY;
-                removed_all++;
-                if (ex >= 0) removed_real++;
-                if (stash) removed_stash++;
+            const u64 p = i + (u64)u * stride;
+            const i64 ea = (i64)(a[u].x + a[u].y), eb = (i64)(b[u].x + b[u].y);
+            const bool xa = ea >= 0 && ea <= now, xb = eb >= 0 && eb <= now;   // entries Store::get no longer shows
+            if (xa | xb) {
+                longlong2 *dst = reinterpret_cast<longlong2 *>(&t.state[2 * p]);
+                dst[0] = xa ? make_longlong2(0, EXP_EMPTY) : make_longlong2((i64)a[u].x, (i64)a[u].y);
+                dst[1] = xb ? make_longlong2(0, EXP_EMPTY) : make_longlong2((i64)b[u].x, (i64)b[u].y);
+                removed += (xa ? 1 : 0) + (xb ? 1 : 0);
             }
         }
         i += (u64)SWEEP_UNROLL * stride;
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        removed_real += __shfl_xor_sync(0xffffffffu, removed_real, o);
-        removed_all += __shfl_xor_sync(0xffffffffu, removed_all, o);
-        removed_stash += __shfl_xor_sync(0xffffffffu, removed_stash, o);
+    removed = __reduce_add_sync(0xffffffffu, removed);
+    if ((threadIdx.x & 31) == 0 && removed) {
+        atomicAdd(&t.counters[C_REAL], (u64)(0 - (u64)removed));
+        atomicAdd(&t.counters[C_SWEPT], (u64)removed);
     }
-    if ((threadIdx.x & 31) == 0 && removed_all) {
-        atomicAdd(&t.counters[C_OCCUPIED], (u64)(0 - (u64)removed_all));
-        atomicAdd(&t.counters[C_REAL], (u64)(0 - (u64)removed_real));
-        atomicAdd(&t.counters[C_SWEPT], (u64)removed_real);
-        if (removed_stash) atomicAdd(&t.counters[C_STASH], (u64)(0 - (u64)removed_stash));
+}
+
+// Reclaim the slots of keys that hold no entry (swept, or only ever denied): exclusive pass run by the host
+// before it would otherwise grow the table.  Reads key + state of every slot, clears such keys
+// (stash: tombstone, so probing continues past them).
+__global__ void __launch_bounds__(TILE_THREADS)
+purge_kernel(Table t, u64 total_slots) {
+    u32 freed = 0, freed_stash = 0;
+    const u64 stride = (u64)gridDim.x * TILE_THREADS;
+    for (u64 k = (u64)blockIdx.x * TILE_THREADS + threadIdx.x; k < total_slots; k += stride) {
+        const ulonglong2 v = ld_stream(&t.state[k]);
+        if ((i64)(v.x + v.y) >= 0) continue;
+        if (t.keys[k] < 2) continue;
+        const bool stash = k >= (u64)t.nb_main * 4;
+        t.keys[k] = stash ? KEY_TOMB : KEY_EMPTY;
+        freed++;
+        if (stash) freed_stash++;
+    }
+    freed = __reduce_add_sync(0xffffffffu, freed);
+    freed_stash = __reduce_add_sync(0xffffffffu, freed_stash);
+    if ((threadIdx.x & 31) == 0 && freed) {
+        atomicAdd(&t.counters[C_OCCUPIED], (u64)(0 - (u64)freed));
+        if (freed_stash) atomicAdd(&t.counters[C_STASH], (u64)(0 - (u64)freed_stash));
     }
 }
 
@@ -924,7 +947,7 @@ rehash_kernel(Table src, u64 src_slots, Table dst) {
         u64 k = src.keys[i];
         if (k < 2) continue;
         TatOff st = src.state[i];
-        if ((i64)((u64)st.tat + st.off) < 0) continue;   // phantoms carry no state
+        if ((i64)((u64)st.tat + st.off) < 0) continue;   // keys without an entry are not carried over
         bool fresh;
         u32 s = find_or_claim(dst, k, fresh);
         if (s == dst.null_slot) { atomicAdd(&dst.counters[C_INSERT_FAIL], 1ULL); continue; }
@@ -958,7 +981,7 @@ __global__ void store_op_kernel(Table t, int op, u64 key, i64 a, i64 b, u64 ttl,
         } else {
             TatOff *l = t.state + s;
             if (fresh) atomicAdd(&t.counters[C_OCCUPIED], 1ULL);
-            i64 ex = fresh ? EXP_PHANTOM : (i64)((u64)l->tat + l->off);
+            i64 ex = (i64)((u64)l->tat + l->off);   // EXP_EMPTY for a fresh or entry-less key
             if (ex > now) {
                 r.flag = 0;                                  // live entry: :264-265
             } else {

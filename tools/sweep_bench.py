@@ -1,8 +1,8 @@
 """K2 (expired-key sweep) on BASELINE.json configs[2]: 100 M keys uniform, sweep at several expired
 fractions; achieved HBM GB/s against MEASURED_PEAKS.json.  Prints one JSON line per sweep.
 
-Algorithmic bytes: 16 B per table slot scanned (tat + burst offset) + 24 B per evicted
-slot (key, tat, offset cleared)."""
+Algorithmic bytes: 16 B per table slot scanned (tat + burst offset) + 16 B per evicted
+entry (the pair reset; keys are reclaimed lazily by purge_kernel)."""
 import argparse
 import json
 import os
@@ -51,7 +51,7 @@ for dt, label in plan:
     before = st.len()
     removed = st.sweep(traces.T0 + dt)
     ms = st.last_sweep_ms()
-    alg = 16.0 * slots + 24.0 * removed
+    alg = 16.0 * slots + 16.0 * removed
     print(json.dumps({"kernel": "sweep_kernel", "keys": args.keys, "table_slots": slots, "live_before": before,
                       "expired": label, "removed": removed, "ms": ms, "achieved_GBps": alg / ms / 1e6,
                       "peak_GBps": peak, "frac": alg / ms / 1e6 / peak}), flush=True)
