@@ -609,8 +609,8 @@ int32_t gcra_create(const gcra_config *cfg, gcra_engine **out) {
     cudaStreamCreateWithFlags(&h->in_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking);
-    // ONE front stream shared by all scratch sets: front halves must not overlap each other (a key claimed
-    // by a later batch's ingest could be decided by an earlier batch before its phantom mark has landed)
+    // ONE front stream shared by all scratch sets (front halves run one after another; since ingest only CASes
+    // the keys array they could overlap as well -- not measured yet)
     cudaStreamCreateWithFlags(&h->front_stream[0], cudaStreamNonBlocking);
     for (int k = 1; k < gcra_engine::N_SCR; k++) h->front_stream[k] = h->front_stream[0];
     cudaStreamCreateWithFlags(&h->back_stream, cudaStreamNonBlocking);
