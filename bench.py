@@ -454,7 +454,11 @@ def main():
         ach = alg_bytes / t_k1 / 1e9
         roof = {"bound": "hbm", "kernel": "K1 = ingest + order + decide (13 launches per tick; consecutive ticks pipelined: front half of tick i+1 overlaps the decide kernels of tick i)",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_kind": peak_kind,
-                "traffic": None,
+                # measured DRAM bytes of one tick's K1 kernels (dram__bytes_read.sum + dram__bytes_write.sum from the
+                # committed `ncu --set full` capture profiles/r01d_ncu_full_k1_raw.csv: ingest 108.7 MB + decide
+                # 105.2 + hot-run kernels 14.9 + 21.4 + 3 x sort_scatter 9.8; sort hist/rowscan were not captured)
+                "traffic": 279.8e6, "traffic_note": "bytes per tick, from profiles/r01d_ncu_full_k1_raw.csv",
+                "algorithmic_bytes_per_tick": alg_bytes / K,
                 "algorithmic_bytes_per_decision": {"allowed": 112, "denied": 96},
                 "serial_tick_phase_ms": {"total": phases[0], "ingest": phases[1], "order": phases[2],
                                        "decide": phases[3]}}
