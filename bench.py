@@ -291,9 +291,15 @@ def main():
         # phase split of ONE tick run serially on the stream (library-side CUDA events); the timed
         # region above pipelines consecutive ticks, so its per-tick time is below this total
         extra = torch.empty(TICK * 32, dtype=torch.uint8, device=dev)
+        if os.environ.get("GCRA_DBG"):          # timing experiments only: this serial tick's results are wrong
+            store._L.gcra_debug_set(store._h, int(os.environ["GCRA_DBG"]))
         lim.rate_limit_batch_device(TICK, d_req[W].data_ptr(), extra.data_ptr(), stream.cuda_stream)
         torch.cuda.synchronize()
         phases = store.last_kernel_ms()
+        try:
+            phase_detail = store.last_kernel_ms_detail()
+        except Exception:
+            phase_detail = None
     # (the clock sampler keeps running through the e2e region: the kernel-only region lasts only a few ms)
 
     # ---------------------------------------------------------------- e2e through the pinned ring
@@ -452,7 +458,8 @@ def main():
     if world == 1:
         t_k1 = total_ms * 1e-3
         ach = alg_bytes / t_k1 / 1e9
-        roof = {"bound": "hbm", "kernel": "K1 = ingest + order + decide (13 launches per tick; consecutive ticks pipelined: front half of tick i+1 overlaps the decide kernels of tick i)",
+        st_k = store.stats()
+        roof = {"bound": "hbm", "kernel": "K1 = probe + note | decide (batch order) + resolve | sorted residue; the three stages of consecutive ticks run on three streams",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_kind": peak_kind,
                 # measured DRAM bytes of one tick's K1 kernels (dram__bytes_read.sum + dram__bytes_write.sum from the
                 # committed `ncu --set full` capture profiles/r01d_ncu_full_k1_raw.csv: ingest 108.7 MB + decide
@@ -460,8 +467,11 @@ def main():
                 "traffic": 279.8e6, "traffic_note": "bytes per tick, from profiles/r01d_ncu_full_k1_raw.csv",
                 "algorithmic_bytes_per_tick": alg_bytes / K,
                 "algorithmic_bytes_per_decision": {"allowed": 112, "denied": 96},
-                "serial_tick_phase_ms": {"total": phases[0], "ingest": phases[1], "order": phases[2],
-                                       "decide": phases[3]}}
+                "serial_tick_phase_ms": {"total": phases[0], "probe+note": phases[1], "decide+resolve": phases[2],
+                                         "sorted_residue": phases[3]},
+                "serial_tick_detail_ms": phase_detail,
+                "residue_fraction": (st_k["residue_rows"] / max(st_k["residue_batches"], 1)) / TICK,
+                "pipeline_drains": st_k["drains"], "index_batches": st_k["index_batches"]}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -40,6 +40,12 @@ enum {
 /* tests only: size the table at 1x capacity and fill it to 15/16 before growing, so that the
  * second-choice buckets, the stash and table growth are exercised by small traces */
 #define GCRA_FLAG_TIGHT_TABLE 1u
+/* tests / A-B measurements: which K1 pipeline a batch takes.  Default: batches of >= 32768 requests take the
+ * index-order pipeline (probe -> decide in batch order -> resolve -> sorted residue), smaller ones the sort
+ * pipeline (ingest -> radix sort by slot -> warp-cooperative decide), <= 255 requests a single-CTA kernel.
+ * INDEX_PATH forces the first for every batch above 255 requests, SORT_PATH disables it. */
+#define GCRA_FLAG_INDEX_PATH 2u
+#define GCRA_FLAG_SORT_PATH 4u
 
 typedef struct gcra_engine gcra_engine;
 
@@ -96,6 +102,9 @@ typedef struct {
     uint64_t sweeps, swept;   /* sweep launches / entries removed */
     uint64_t grows;
     uint64_t purges;          /* passes that reclaimed the slots of keys without an entry */
+    /* index-order K1 pipeline: batches it carried; residue rows (requests that went through the sorted tail) summed
+     * over the `residue_batches` batches whose count has reached the host; times stage 2 waited for every tail */
+    uint64_t index_batches, residue_rows, residue_batches, drains;
 } gcra_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------- */
@@ -184,6 +193,13 @@ int32_t gcra_sync(gcra_engine *h);
 /* device time (ms) of the kernels of the most recent batch call, measured with CUDA events on
  * the launching stream: [0] total, [1] ingest (hash probe), [2] sort, [3] decide */
 int32_t gcra_last_kernel_ms(gcra_engine *h, float out[4]);
+/* the most recent batch that took the index-order pipeline on ONE stream (gcra_rate_limit_batch_device): device
+ * time (ms) of [0] probe, [1] note, [2] decide in batch order, [3] resolve, [4] bitmap clear + residue-count copy,
+ * [5] residue radix sort, [6] residue decide + hot-run kernels */
+int32_t gcra_last_kernel_ms_detail(gcra_engine *h, float out[7]);
+/* timing experiments only (tools/): a non-zero mask makes pass B of the index-order pipeline skip parts of its work
+ * -- results are then WRONG; never set outside a profiling session */
+void gcra_debug_set(gcra_engine *h, uint32_t mask);
 /* device time (ms) of the most recent sweep kernel (CUDA events on the launching stream) */
 int32_t gcra_last_sweep_ms(gcra_engine *h, float *ms);
 /* number of kernels this handle has launched since creation */

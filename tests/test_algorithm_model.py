@@ -125,3 +125,61 @@ def test_toggling_key_needs_few_finite_state_rounds():
     assert fsm_rounds(run, None, stride=64) == want
     assert speculate_commit(run, None) == want
     assert len({o for o in want[0]}) > 2          # allowed and denied outcomes really alternate
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the index-order pipeline (csrc/gcra_index_path.cuh): probe -> decide against the batch-start state -> resolve
+# -> sequential residue, over a batch that mixes several keys; `entries` models the hashed batch bitmap (two
+# keys may share an entry: both are then treated as shared, which must not change any result)
+# ---------------------------------------------------------------------------------------------------------
+def index_order_pipeline(batch, table, entries=4):
+    """batch = [(key, req)], table = {key: state}.  Returns (outputs per row, table after the batch)."""
+    table = dict(table)
+    seen, shared = set(), set()
+    for key, _ in batch:                                         # pass A: the batch bitmap
+        e = key % entries
+        (shared if e in seen else seen).add(e)
+    outs, first_change, verdict = [None] * len(batch), {}, {}
+    for i, (key, r) in enumerate(batch):                         # pass B (any order: reads batch-start states only)
+        s0 = table.get(key)
+        _, ns, o = decide(s0, r)
+        outs[i] = o
+        if key % entries not in shared:
+            table[key] = ns                                      # alone on its key: commit
+        else:
+            verdict[i] = ns != s0
+    for i in sorted(verdict, reverse=True):                      # atomicMin(mark[slot]), any order
+        if verdict[i]:
+            first_change[batch[i][0]] = i
+    residue = []
+    commits = {}
+    for i in verdict:                                            # pass C
+        key = batch[i][0]
+        fm = first_change.get(key)
+        if fm is not None and i > fm:
+            residue.append(i)
+        elif fm == i:
+            commits[key] = decide(table.get(key), batch[i][1])[1]
+    table.update(commits)
+    for i in sorted(residue):                                    # residue: one after another, in batch order
+        key, r = batch[i]
+        _, table[key], outs[i] = decide(table.get(key), r)
+    return outs, table
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.lists(st.tuples(st.integers(0, 9), req), min_size=1, max_size=150), st.integers(1, 7))
+def test_index_order_pipeline_equals_sequential(rows, entries):
+    now, batch = T0, []
+    for key, ((b, c, p), q, d) in rows:
+        now += d
+        _, ei, dvt = derive(b, c, p)
+        batch.append((key, (now, ei, dvt, q)))
+    table0 = {k: (T0 - 10**9, T0 + 5 * 10**9) for k in range(0, 10, 3)}
+    want_outs, want_table = [], dict(table0)
+    for key, r in batch:
+        _, want_table[key], o = decide(want_table.get(key), r)
+        want_outs.append(o)
+    outs, table = index_order_pipeline(batch, table0, entries)
+    assert outs == want_outs
+    assert {k: v for k, v in table.items() if v is not None} == {k: v for k, v in want_table.items() if v is not None}

@@ -241,6 +241,12 @@ class _GpuStore:
         self._check(self._L.gcra_last_kernel_ms(self._h, C.byref(out)))
         return [float(x) for x in out]
 
+    def last_kernel_ms_detail(self):
+        out = (C.c_float * 7)()
+        self._check(self._L.gcra_last_kernel_ms_detail(self._h, C.byref(out)))
+        return dict(zip(("probe", "note", "decide_index", "resolve", "clear", "residue_sort", "residue_decide"),
+                        [float(x) for x in out]))
+
     def last_sweep_ms(self):
         ms = C.c_float()
         self._check(self._L.gcra_last_sweep_ms(self._h, C.byref(ms)))

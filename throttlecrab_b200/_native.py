@@ -28,6 +28,7 @@ assert REQ_DTYPE.itemsize == 48 and RES_DTYPE.itemsize == 32 and REQ16_DTYPE.ite
 
 OK, NEGATIVE_QUANTITY, INVALID_RATE_LIMIT, INTERNAL = 0, 1, 2, 3
 STORE_PERIODIC, STORE_PROBABILISTIC, STORE_ADAPTIVE, STORE_MANUAL = 0, 1, 2, 3
+FLAG_TIGHT_TABLE, FLAG_INDEX_PATH, FLAG_SORT_PATH = 1, 2, 4
 
 
 class Config(C.Structure):
@@ -39,7 +40,8 @@ class Config(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in
                 ("len", "occupied_slots", "table_slots", "stash_entries", "allowed", "denied",
-                 "errors", "expired_hits", "sweeps", "swept", "grows", "purges")]
+                 "errors", "expired_hits", "sweeps", "swept", "grows", "purges",
+                 "index_batches", "residue_rows", "residue_batches", "drains")]
 
 
 def sources():
@@ -97,6 +99,8 @@ SYMBOLS = {
     "gcra_snapshot_load": (_i32, [_vp, C.c_char_p]),
     "gcra_sync": (_i32, [_vp]),
     "gcra_last_kernel_ms": (_i32, [_vp, C.POINTER(C.c_float * 4)]),
+    "gcra_last_kernel_ms_detail": (_i32, [_vp, C.POINTER(C.c_float * 7)]),
+    "gcra_debug_set": (None, [_vp, _u32]),
     "gcra_last_sweep_ms": (_i32, [_vp, C.POINTER(C.c_float)]),
     "gcra_launch_count": (_u64, [_vp]),
     "gcra_shard_unique_ids": (_i32, [_vp]),

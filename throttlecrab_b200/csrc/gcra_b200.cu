@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "gcra_kernels.cuh"
+#include "gcra_index_path.cuh"
 
 using namespace gcra;
 
@@ -127,8 +128,18 @@ struct Scratch {
     u32 *hist = nullptr, *tot = nullptr;
     LongRun *long_runs = nullptr, *giant_runs = nullptr;
     u32 *long_count = nullptr;
-    cudaEvent_t ev_front = nullptr, ev_back = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_front = nullptr, ev_mid = nullptr, ev_back = nullptr, ev_fork = nullptr, ev_join = nullptr;
     bool back_recorded = false;
+    // index-order pipeline (gcra_index_path.cuh)
+    u32 *slot_arr = nullptr;            // [rows] slot of every row (null slot: the row failed validation)
+    unsigned char *flags = nullptr;     // [rows] pass-B verdict of rows on shared slots
+    u32 *bitmap = nullptr;              // [bm_words] 2 bits per entry: seen / seen twice
+    u64 *ctrl_block = nullptr;          // word 0: {tile ticket, residue count}; word 1: {sort barrier, -}; then one status word per tile
+    u32 *ridx = nullptr;                // [rows] residue position -> row id
+    uint32_t rows_alloc = 0;
+    u32 *h_nres = nullptr;              // pinned: residue size of the set's latest index-order batch (valid after ev_mid)
+    bool mid_recorded = false, nres_counted = true;
+    uint32_t nres_rows = 0;             // rows of that batch
 };
 
 struct gcra_engine {
@@ -141,12 +152,15 @@ struct gcra_engine {
     // scratch for one batch
     uint32_t max_batch = 0;
 #ifndef GCRA_PIPE_SETS
-#define GCRA_PIPE_SETS 2
+#define GCRA_PIPE_SETS 4
 #endif
     static const int N_SCR = GCRA_PIPE_SETS;
     Scratch scr[N_SCR];
     uint32_t scr_next = 0;
-    cudaStream_t front_stream[N_SCR] = {}, back_stream = nullptr;   // pipelined submission
+    // pipelined submission: three stages on three streams (front: probe | mid: decide + resolve | tail: the
+    // sorted residue); the sort pipeline uses front (ingest + sort) and mid (decide)
+    cudaStream_t front_stream[N_SCR] = {}, back_stream = nullptr, tail_stream = nullptr;
+    int pend_set = -1;               // scratch set whose bitmap holds the PEND bits of the batch submitted last (-1: none)
     cudaEvent_t ev_ready = nullptr;
     void *d_req = nullptr;
     gcra_result *d_res = nullptr;
@@ -157,6 +171,8 @@ struct gcra_engine {
     u64 *h_counters = nullptr;       // pinned snapshot, refreshed after every batch
     cudaEvent_t ev_counters = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t evd[8] = {};         // index-order pipeline, serial timed batch: after each kernel group
+    bool evd_valid = false;
     cudaEvent_t ev_sweep[2] = {nullptr, nullptr};
     bool sweep_timed = false;
     bool ev_valid = false;
@@ -180,12 +196,25 @@ struct gcra_engine {
     uint64_t seen_allowed = 0, seen_expired_hits = 0;
     uint64_t n_sweeps = 0, n_grows = 0, n_purges = 0;
     Shard *shard = nullptr;          // multi-GPU: native NCCL pipeline (gcra_shard_*)
+    // index-order pipeline
+    uint32_t epoch = 0;              // batch epoch of the slot marks (never 0)
+    uint32_t bm_mask = 0;            // bitmap entries - 1
+    size_t bm_words = 0;
+    uint32_t index_min = 0;          // batches of at least this many rows take the index-order pipeline (0: never)
+    int prefetch_state = 0;
+    uint32_t max_tiles = 0;
+    uint32_t grid_probe[2] = {592, 592}, grid_decide[2] = {444, 444};   // resident CTAs of the persistent kernels [compact]
+    uint32_t dbg = 0;                // timing experiments only (gcra_debug_set): skips parts of pass B
+    uint32_t since_drain = 0;        // index-order batches submitted since stage 2 last waited for every tail
+    uint64_t n_drains = 0, n_index_batches = 0, residue_seen = 0, residue_batches_seen = 0;
     // ring
     std::vector<RingSlot> ring;
     uint32_t ring_cap = 0;
     bool ring_compact = false;
     std::string err;
 };
+
+static int alloc_index_scratch(gcra_engine *h, Scratch &sc, uint32_t rows);
 
 static uint32_t ceil_log2(uint64_t x) {
     uint32_t b = 0;
@@ -209,6 +238,8 @@ static int alloc_table(gcra_engine *h, uint64_t capacity, Table &t, uint32_t &to
     CK(cudaMalloc(&t.keys, slots * sizeof(u64)));
     CK(cudaMalloc(&t.state, slots * sizeof(TatOff)));
     CK(cudaMalloc(&t.ei, slots * sizeof(i64)));
+    CK(cudaMalloc(&t.mark, slots * sizeof(u64)));
+    CK(cudaMemsetAsync(t.mark, 0xff, slots * sizeof(u64), h->stream));   // no batch epoch matches
     t.nb_main = nb;
     t.stash_slots = ss;
     t.null_slot = total_lines * 4 - 1;
@@ -312,7 +343,7 @@ static int grow(gcra_engine *h, uint64_t need) {
     keep[C_STASH] = fresh[C_STASH];
     CK(cudaMemcpyAsync(ncounters, keep, sizeof(keep), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(h->tab.keys); cudaFree(h->tab.state); cudaFree(h->tab.ei);
+    cudaFree(h->tab.keys); cudaFree(h->tab.state); cudaFree(h->tab.ei); cudaFree(h->tab.mark);
     cudaFree(h->tab.counters);
     h->tab = nt;
     h->total_lines = nl;
@@ -437,7 +468,7 @@ static int apply_policy(gcra_engine *h, int64_t now_ns) {
 }
 
 // the cluster kernel: cluster dimension given at launch (cudaLaunchKernelEx)
-static int launch_giant(gcra_engine *h, Scratch &sc, const u64 *src, gcra_result *d_res, cudaStream_t st) {
+static int launch_giant(gcra_engine *h, Scratch &sc, const u64 *src, const OutMap &om, cudaStream_t st) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((128 / CLUSTER_CTAS) * CLUSTER_CTAS);
     cfg.blockDim = dim3(LONG_THREADS);
@@ -453,68 +484,209 @@ static int launch_giant(gcra_engine *h, Scratch &sc, const u64 *src, gcra_result
         static bool once = false;
         if (!once) { cudaFuncSetAttribute(decide_runs_kernel<CLUSTER_CTAS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); once = true; }
     }
-    CK(cudaLaunchKernelEx(&cfg, decide_runs_kernel<CLUSTER_CTAS>, h->tab, (const u64 *)src, (const Req *)sc.drec, d_res,
+    CK(cudaLaunchKernelEx(&cfg, decide_runs_kernel<CLUSTER_CTAS>, h->tab, (const u64 *)src, (const Req *)sc.drec, om,
                           (const LongRun *)sc.giant_runs, (const u32 *)(sc.long_count + 1)));
     return GCRA_OK;
 }
 
-// front half of a batch: ingest (validate, derive, probe/claim) + stable sort by slot.  Independent of the
-// back half of EARLIER batches: it only claims empty slots (keys array, phantom mark in their state),
-// which no earlier batch's decide kernels touch.
-static int enqueue_front(gcra_engine *h, Scratch &sc, uint32_t n, const void *d_req, bool compact, int64_t now_batch,
-                         gcra_result *d_res, cudaStream_t st, bool timed, u64 **sorted_out) {
-    const uint32_t tiles = (n + TILE_THREADS - 1) / TILE_THREADS;
-    if (timed) CK(cudaEventRecord(h->ev[0], st));
-    if (compact)
-        ingest_kernel<true><<<tiles, TILE_THREADS, 0, st>>>(h->tab, d_req, h->d_pol, h->npol, now_batch, n,
-                                                            sc.drec, sc.keys_a, d_res);
-    else
-        ingest_kernel<false><<<tiles, TILE_THREADS, 0, st>>>(h->tab, d_req, nullptr, 0, 0, n, sc.drec,
-                                                             sc.keys_a, d_res);
-    h->launches++;
-    if (timed) CK(cudaEventRecord(h->ev[1], st));
-    // stable LSD radix sort over the slot bits
+static BatchView single_view(const void *d_req, gcra_result *d_res, uint32_t n) {
+    BatchView v{};
+    v.req0 = (const unsigned char *)d_req;
+    v.res0 = d_res;
+    v.n = n;
+    v.nseg = 1;
+    v.cap_shift = 31;
+    return v;
+}
+
+// stable LSD radix sort of `n` (host count) or `*n_dev` (device count) keys on the slot bits; returns the buffer
+// that holds the sorted keys
+static int enqueue_sort(gcra_engine *h, Scratch &sc, uint32_t n_max, const u32 *n_dev, cudaStream_t st, u64 **sorted_out) {
     const uint32_t bits = h->tab.slot_bits;
     const uint32_t passes = (bits + SORT_MAX_BITS - 1) / SORT_MAX_BITS;
-    const uint32_t stiles = (n + SORT_TILE - 1) / SORT_TILE;
+    uint32_t stiles = (n_max + SORT_TILE - 1) / SORT_TILE;
+    if (n_dev) stiles = std::min<uint32_t>(stiles, 2 * 148);      // fixed grid, all CTAs resident: the kernels loop over the tiles
     u64 *src = sc.keys_a, *dst = sc.keys_b;
     uint32_t shift = 32;
     for (uint32_t p = 0; p < passes; p++) {
         uint32_t pb = bits / passes + (p < bits % passes ? 1 : 0);
-        sort_hist_kernel<<<stiles, TILE_THREADS, 0, st>>>(src, n, shift, pb, stiles, sc.hist);
-        sort_rowscan_kernel<<<1u << pb, TILE_THREADS, 0, st>>>(sc.hist, stiles, sc.tot);
-        sort_scatter_kernel<<<stiles, TILE_THREADS, 0, st>>>(src, dst, n, shift, pb, stiles, sc.hist, sc.tot);
-        h->launches += 3;
+        if (n_dev) {
+            // device-side count (the residue): one launch per pass, grid barriers between its phases
+            u32 *bar_cnt = reinterpret_cast<u32 *>(sc.ctrl_block + 1);
+            sort_pass_fused_kernel<<<stiles, TILE_THREADS, 0, st>>>(src, dst, n_dev, shift, pb, sc.hist, sc.tot, bar_cnt, p);
+            h->launches++;
+        } else {
+            sort_hist_kernel<<<stiles, TILE_THREADS, 0, st>>>(src, n_max, n_dev, shift, pb, sc.hist);
+            sort_rowscan_kernel<<<1u << pb, TILE_THREADS, 0, st>>>(sc.hist, n_max, n_dev, sc.tot);
+            sort_scatter_kernel<<<stiles, TILE_THREADS, 0, st>>>(src, dst, n_max, n_dev, shift, pb, sc.hist, sc.tot);
+            h->launches += 3;
+        }
         std::swap(src, dst);
         shift += pb;
     }
-    if (timed) CK(cudaEventRecord(h->ev[2], st));
-    CK(cudaMemsetAsync(sc.long_count, 0, 2 * sizeof(u32), st));
     *sorted_out = src;
     return GCRA_OK;
 }
 
-// back half: the compare-and-update kernels; batches' back halves run strictly in submission order
-static int enqueue_back(gcra_engine *h, Scratch &sc, uint32_t n, const u64 *src, gcra_result *d_res, cudaStream_t st,
-                        bool timed) {
-    const uint32_t warps = (n + 31) / 32;
-    decide_kernel<<<(warps + DECIDE_THREADS / 32 - 1) / (DECIDE_THREADS / 32), DECIDE_THREADS, 0, st>>>(
-        h->tab, src, sc.drec, n, d_res, sc.long_runs, sc.giant_runs, sc.long_count);
+// the warp-cooperative compare-and-update over sorted keys + the hot-run kernels
+static int enqueue_decide_sorted(gcra_engine *h, Scratch &sc, uint32_t n_max, const u32 *n_dev, const u64 *src,
+                                 const OutMap &om, cudaStream_t st) {
+    CK(cudaMemsetAsync(sc.long_count, 0, 2 * sizeof(u32), st));
+    const uint32_t warps = (n_max + 31) / 32;
+    uint32_t grid = (warps + DECIDE_THREADS / 32 - 1) / (DECIDE_THREADS / 32);
+    if (n_dev) grid = std::min<uint32_t>(grid, 4 * 148);
+    decide_kernel<<<grid, DECIDE_THREADS, 0, st>>>(h->tab, src, sc.drec, n_max, n_dev, om, sc.long_runs, sc.giant_runs,
+                                                   sc.long_count);
     h->launches++;
-    if (n >= GIANT_RUN_MIN) {
+    if (n_max >= GIANT_RUN_MIN) {
         // the two hot-run kernels work on disjoint runs: the one-CTA-per-run kernel goes to a side
         // stream and overlaps the cluster kernel (fork/join with events)
         CK(cudaEventRecord(sc.ev_fork, st));
         CK(cudaStreamWaitEvent(h->aux_stream, sc.ev_fork, 0));
-        decide_runs_kernel<1><<<148, LONG_THREADS, 0, h->aux_stream>>>(h->tab, src, sc.drec, d_res, sc.long_runs, sc.long_count);
+        decide_runs_kernel<1><<<148, LONG_THREADS, 0, h->aux_stream>>>(h->tab, src, sc.drec, om, sc.long_runs, sc.long_count);
         CK(cudaEventRecord(sc.ev_join, h->aux_stream));
-        RC(launch_giant(h, sc, src, d_res, st));   // hottest keys: one cluster per run
+        RC(launch_giant(h, sc, src, om, st));   // hottest keys: one cluster per run
         CK(cudaStreamWaitEvent(st, sc.ev_join, 0));
         h->launches += 2;
-    } else if (n >= LONG_RUN_MIN) {
-        decide_runs_kernel<1><<<148, LONG_THREADS, 0, st>>>(h->tab, src, sc.drec, d_res, sc.long_runs, sc.long_count);
+    } else if (n_max >= LONG_RUN_MIN) {
+        decide_runs_kernel<1><<<148, LONG_THREADS, 0, st>>>(h->tab, src, sc.drec, om, sc.long_runs, sc.long_count);
         h->launches++;
     }
+    return GCRA_OK;
+}
+
+// per-set buffers of the index-order pipeline for batches of up to `rows` row ids
+static int alloc_index_scratch(gcra_engine *h, Scratch &sc, uint32_t rows) {
+    cudaFree(sc.slot_arr); cudaFree(sc.flags); cudaFree(sc.ridx); cudaFree(sc.ctrl_block);
+    sc.slot_arr = nullptr; sc.flags = nullptr; sc.ridx = nullptr; sc.ctrl_block = nullptr;
+    const uint32_t tiles = (rows + TILE_THREADS - 1) / TILE_THREADS;
+    if (tiles > h->max_tiles) h->max_tiles = tiles;
+    CK(cudaMalloc(&sc.slot_arr, (size_t)rows * sizeof(u32)));
+    CK(cudaMalloc(&sc.flags, (size_t)rows));
+    CK(cudaMalloc(&sc.ridx, (size_t)h->max_batch * sizeof(u32)));
+    CK(cudaMalloc(&sc.ctrl_block, ((size_t)h->max_tiles + 2) * sizeof(u64)));
+    if (!sc.h_nres) { CK(cudaMallocHost(&sc.h_nres, sizeof(u32))); *sc.h_nres = 0; }
+    if (!sc.bitmap) {
+        CK(cudaMalloc(&sc.bitmap, h->bm_words * sizeof(u32)));
+        CK(cudaMemsetAsync(sc.bitmap, 0, h->bm_words * sizeof(u32), h->stream));   // from then on cleared after every use
+    }
+    sc.rows_alloc = rows;
+    return GCRA_OK;
+}
+
+static bool use_index_path(const gcra_engine *h, uint32_t n) { return h->index_min != 0 && n >= h->index_min; }
+
+static uint32_t view_max_rows(const BatchView &v) { return v.nseg == 1 ? v.n : (v.nseg << v.cap_shift); }
+
+// Stage 1 of a batch.  Independent of the later stages of EARLIER batches: it only claims empty slots (a CAS on
+// the keys array; it never touches the state array), which no earlier batch's decide kernels touch.
+//   sort pipeline         ingest (validate, derive, probe/claim) + stable sort by slot
+//   index-order pipeline  pass A (probe) + pass A' (batch bitmap)
+static int enqueue_front(gcra_engine *h, Scratch &sc, const BatchView &v, bool index_path, bool compact, int64_t now_batch,
+                         cudaStream_t st, bool timed, u64 **sorted_out) {
+    if (timed) CK(cudaEventRecord(h->ev[0], st));
+    *sorted_out = nullptr;
+    if (index_path) {
+        const uint32_t rows = view_max_rows(v);
+        const uint32_t tiles = (rows + TILE_THREADS - 1) / TILE_THREADS;
+        const uint32_t grid = std::min<uint32_t>(tiles, h->grid_probe[compact ? 1 : 0]);    // persistent, software-pipelined CTAs
+        CK(cudaMemsetAsync(sc.ctrl_block, 0, ((size_t)h->max_tiles + 2) * sizeof(u64), st));
+        if (timed) CK(cudaEventRecord(h->evd[0], st));
+        if (compact)
+            probe_kernel<true><<<grid, TILE_THREADS, 0, st>>>(h->tab, v, h->d_pol, h->npol, now_batch, sc.slot_arr,
+                                                              h->prefetch_state);
+        else
+            probe_kernel<false><<<grid, TILE_THREADS, 0, st>>>(h->tab, v, nullptr, 0, 0, sc.slot_arr, h->prefetch_state);
+        if (timed) CK(cudaEventRecord(h->evd[1], st));
+        note_kernel<<<std::min<uint32_t>(tiles, 16 * 148), TILE_THREADS, 0, st>>>(v, h->tab.null_slot, sc.slot_arr, sc.bitmap, h->bm_mask);
+        h->launches += 2;
+        if (timed) { CK(cudaEventRecord(h->ev[1], st)); CK(cudaEventRecord(h->evd[2], st)); }
+        return GCRA_OK;
+    }
+    const uint32_t n = v.n;
+    const uint32_t tiles = (n + TILE_THREADS - 1) / TILE_THREADS;
+    if (compact)
+        ingest_kernel<true><<<tiles, TILE_THREADS, 0, st>>>(h->tab, v.req0, h->d_pol, h->npol, now_batch, n,
+                                                            sc.drec, sc.keys_a, v.res0);
+    else
+        ingest_kernel<false><<<tiles, TILE_THREADS, 0, st>>>(h->tab, v.req0, nullptr, 0, 0, n, sc.drec,
+                                                             sc.keys_a, v.res0);
+    h->launches++;
+    if (timed) CK(cudaEventRecord(h->ev[1], st));
+    RC(enqueue_sort(h, sc, n, nullptr, st, sorted_out));
+    if (timed) CK(cudaEventRecord(h->ev[2], st));
+    return GCRA_OK;
+}
+
+// Stage 2 of an index-order batch: pass B (decide in batch order) + pass C (resolve).  Batches' stages 2 run
+// strictly in submission order.  `next` is the scratch set the NEXT batch will use: pass C leaves the PEND bits
+// of this batch's residue keys in its bitmap.  This set's own bitmap is cleared for its next use afterwards.
+static int enqueue_mid_index(gcra_engine *h, Scratch &sc, Scratch &next, const BatchView &v, bool compact, int64_t now_batch,
+                             bool honour_pend, cudaStream_t st, bool timed) {
+    const u32 pend_mask = honour_pend ? 0xFu : (0xFu & ~BM_PEND);
+    if (++h->epoch == 0) {
+        // the 32-bit batch epoch wrapped: forget every mark (once per 4 G batches)
+        CK(cudaMemsetAsync(h->tab.mark, 0xff, (size_t)h->total_lines * 4 * sizeof(u64), st));
+        h->epoch = 1;
+    }
+    const uint32_t rows = view_max_rows(v);
+    const uint32_t grid = std::min<uint32_t>((rows + TILE_THREADS - 1) / TILE_THREADS, h->grid_decide[compact ? 1 : 0]);   // persistent CTAs
+    const uint32_t rgrid = std::min<uint32_t>((rows + RES_TILE - 1) / RES_TILE + v.nseg, 6 * 148);
+    u32 *ctrl = reinterpret_cast<u32 *>(sc.ctrl_block);
+    u64 *status = sc.ctrl_block + 2;
+    if (compact) {
+        decide_index_kernel<true><<<grid, TILE_THREADS, 0, st>>>(h->tab, v, h->d_pol, h->npol, now_batch, sc.slot_arr,
+                                                                 sc.bitmap, h->bm_mask, sc.flags, h->epoch, pend_mask, h->dbg);
+        resolve_kernel<true><<<rgrid, TILE_THREADS, 0, st>>>(h->tab, v, h->d_pol, h->npol, now_batch, sc.slot_arr, sc.bitmap,
+                                                             h->bm_mask, sc.flags, h->epoch, ctrl, status, sc.keys_a,
+                                                             sc.ridx, sc.drec, next.bitmap, pend_mask, sc.h_nres);
+    } else {
+        decide_index_kernel<false><<<grid, TILE_THREADS, 0, st>>>(h->tab, v, nullptr, 0, 0, sc.slot_arr, sc.bitmap,
+                                                                  h->bm_mask, sc.flags, h->epoch, pend_mask, h->dbg);
+        if (timed) CK(cudaEventRecord(h->evd[3], st));
+        resolve_kernel<false><<<rgrid, TILE_THREADS, 0, st>>>(h->tab, v, nullptr, 0, 0, sc.slot_arr, sc.bitmap, h->bm_mask,
+                                                              sc.flags, h->epoch, ctrl, status, sc.keys_a, sc.ridx,
+                                                              sc.drec, next.bitmap, pend_mask, sc.h_nres);
+    }
+    h->launches += 2;
+    h->n_index_batches++;
+    if (timed) CK(cudaEventRecord(h->evd[4], st));
+    CK(cudaMemsetAsync(sc.bitmap, 0, h->bm_words * sizeof(u32), st));
+    // (pass C wrote the residue size of this batch to sc.h_nres, mapped pinned host memory: read, once ev_mid has
+    // completed, when later batches are submitted)
+    sc.nres_rows = std::min<uint32_t>(rows, h->max_batch);
+    sc.nres_counted = false;
+    if (timed) CK(cudaEventRecord(h->ev[2], st));
+    CK(cudaGetLastError());
+    return GCRA_OK;
+}
+
+// Stage 3 of an index-order batch: the residue (requests behind the first state change of their key, and
+// requests deferred because the previous batch's tail still owned their key) through the sort pipeline; its
+// size only exists on the device.  Tails run strictly in submission order.
+static int enqueue_tail_index(gcra_engine *h, Scratch &sc, const BatchView &v, cudaStream_t st, bool timed) {
+    const u32 *n_res = reinterpret_cast<const u32 *>(sc.ctrl_block) + RC_NRES;
+    const uint32_t n_max = std::min<uint32_t>(view_max_rows(v), h->max_batch);
+    u64 *rs = nullptr;
+    if (timed) CK(cudaEventRecord(h->evd[5], st));
+    RC(enqueue_sort(h, sc, n_max, n_res, st, &rs));
+    if (timed) CK(cudaEventRecord(h->evd[6], st));
+    OutMap om{};
+    om.out = nullptr;
+    om.ridx = sc.ridx;
+    om.view = v;
+    RC(enqueue_decide_sorted(h, sc, n_max, n_res, rs, om, st));
+    if (timed) { CK(cudaEventRecord(h->ev[3], st)); h->ev_valid = true; CK(cudaEventRecord(h->evd[7], st)); h->evd_valid = true; }
+    CK(cudaGetLastError());
+    return GCRA_OK;
+}
+
+// Stage 2 of a sort-pipeline batch: the compare-and-update kernels over the sorted keys
+static int enqueue_back_sorted(gcra_engine *h, Scratch &sc, const BatchView &v, const u64 *sorted, cudaStream_t st, bool timed) {
+    OutMap om{};
+    om.out = v.res0;
+    om.ridx = nullptr;
+    RC(enqueue_decide_sorted(h, sc, v.n, nullptr, sorted, om, st));
     if (timed) { CK(cudaEventRecord(h->ev[3], st)); h->ev_valid = true; }
     CK(cudaGetLastError());
     return GCRA_OK;
@@ -531,8 +703,10 @@ static int launch_batch(gcra_engine *h, uint32_t n, const void *d_req, bool comp
                         gcra_result *d_res, cudaStream_t st, bool timed) {
     if (n == 0) return GCRA_OK;
     RC(check_batch(h, n, compact));
-    Scratch &sc = h->scr[h->scr_next];
+    const uint32_t k = h->scr_next;
+    Scratch &sc = h->scr[k];
     h->scr_next = (h->scr_next + 1) % gcra_engine::N_SCR;
+    Scratch &next = h->scr[h->scr_next];
     // order after every earlier batch (they may have been submitted pipelined on the engine's streams),
     // which also frees this scratch set
     for (auto &o : h->scr) if (o.back_recorded) CK(cudaStreamWaitEvent(st, o.ev_back, 0));
@@ -550,38 +724,96 @@ static int launch_batch(gcra_engine *h, uint32_t n, const void *d_req, bool comp
         CK(cudaGetLastError());
     } else {
         u64 *sorted = nullptr;
-        RC(enqueue_front(h, sc, n, d_req, compact, now_batch, d_res, st, timed, &sorted));
-        RC(enqueue_back(h, sc, n, sorted, d_res, st, timed));
+        const BatchView v = single_view(d_req, d_res, n);
+        const bool ip = use_index_path(h, n);
+        RC(enqueue_front(h, sc, v, ip, compact, now_batch, st, timed, &sorted));
+        if (ip) {
+            RC(enqueue_mid_index(h, sc, next, v, compact, now_batch, false, st, timed));
+            CK(cudaEventRecord(sc.ev_mid, st));
+            sc.mid_recorded = true;
+            RC(enqueue_tail_index(h, sc, v, st, timed));
+        } else {
+            RC(enqueue_back_sorted(h, sc, v, sorted, st, timed));
+        }
     }
     CK(cudaEventRecord(sc.ev_back, st));
     sc.back_recorded = true;
+    h->pend_set = -1;          // everything of this batch is ordered on `st`: the next batch waits for all of it
     return snapshot_async(h, n, st);
 }
 
-// ---- one batch, pipelined: front half on front_stream, back half on back_stream ------------------
-// The front half of this batch overlaps the back half of the previous one.  `ready` (may be null) is an
-// event after which d_req may be read; `*done` is set to an event after which d_res is complete.
-static int launch_pipelined(gcra_engine *h, uint32_t n, const void *d_req, bool compact, int64_t now_batch,
-                            gcra_result *d_res, cudaEvent_t ready, cudaEvent_t *done) {
-    if (n == 0) { if (done) *done = nullptr; return GCRA_OK; }
-    RC(check_batch(h, n, compact));
+// ---- one batch, pipelined over the engine's streams --------------------------------------------------
+// index-order pipeline: stage 1 (probe) of batch j+1 overlaps stage 2 (decide, resolve) of batch j and stage 3
+// (the sorted residue) of batch j-1.  Stage 2 of batch j may run while the tail of batch j-1 is still at work
+// because pass C of batch j-1 left PEND bits for exactly the keys that tail owns.  Sort pipeline: stage 1 =
+// ingest + sort, stage 2 = decide, after every earlier batch has completely finished.
+// `ready` (may be null) is an event after which the requests may be read; `*done` is set to an event after which
+// the results are complete.
+static int launch_pipelined_view(gcra_engine *h, const BatchView &v, uint32_t n_rows, bool compact, int64_t now_batch,
+                                 cudaEvent_t ready, cudaEvent_t *done) {
+    RC(check_batch(h, n_rows, compact));
     const uint32_t k = h->scr_next;
     Scratch &sc = h->scr[k];
     h->scr_next = (h->scr_next + 1) % gcra_engine::N_SCR;
+    const uint32_t kn = h->scr_next;
     cudaStream_t fs = h->front_stream[k];                  // (all sets share one front stream, see gcra_create)
     if (ready) CK(cudaStreamWaitEvent(fs, ready, 0));
     if (sc.back_recorded) CK(cudaStreamWaitEvent(fs, sc.ev_back, 0));   // scratch set free again
     u64 *sorted = nullptr;
-    RC(enqueue_front(h, sc, n, d_req, compact, now_batch, d_res, fs, false, &sorted));
+    const bool ip = v.nseg > 1 || use_index_path(h, n_rows);
+    RC(enqueue_front(h, sc, v, ip, compact, now_batch, fs, false, &sorted));
     CK(cudaEventRecord(sc.ev_front, fs));
-    CK(cudaStreamWaitEvent(h->back_stream, sc.ev_front, 0));
-    // decisions strictly in submission order, also after batches submitted on a caller stream
-    for (auto &o : h->scr) if (&o != &sc && o.back_recorded) CK(cudaStreamWaitEvent(h->back_stream, o.ev_back, 0));
-    RC(enqueue_back(h, sc, n, sorted, d_res, h->back_stream, false));
-    CK(cudaEventRecord(sc.ev_back, h->back_stream));
+    cudaStream_t ms = h->back_stream;
+    CK(cudaStreamWaitEvent(ms, sc.ev_front, 0));
+    // May stage 2 of this batch overlap the tail of the batch submitted just before?  Only if that batch left its
+    // PEND bits in this set's bitmap.  Keys the tail owns stay deferred for as long as they keep appearing (their
+    // requests go from tail to tail), so the overlap is given up -- stage 2 waits for every tail and ignores the
+    // PEND bits -- whenever the residue reported by an earlier batch has grown beyond 1/8 of its rows, and every
+    // 64 batches.
+    bool overlap = ip && h->pend_set == (int)k;
+    if (ip) {
+        for (int back = 1; back < gcra_engine::N_SCR; back++) {
+            Scratch &os = h->scr[(k + gcra_engine::N_SCR - back) % gcra_engine::N_SCR];
+            if (!os.mid_recorded || cudaEventQuery(os.ev_mid) != cudaSuccess) continue;
+            if (!os.nres_counted) { h->residue_seen += *os.h_nres; h->residue_batches_seen++; os.nres_counted = true; }
+            if ((uint64_t)*os.h_nres * 8 > os.nres_rows && h->since_drain >= 2) overlap = false;
+            break;
+        }
+        if (h->since_drain >= 64) overlap = false;
+        if (!overlap) { if (h->pend_set == (int)k) h->n_drains++; h->since_drain = 0; } else h->since_drain++;
+    }
+    for (int o = 0; o < gcra_engine::N_SCR; o++) {
+        Scratch &os = h->scr[o];
+        if (o == (int)k || !os.back_recorded) continue;
+        const bool is_prev = o == (int)((k + gcra_engine::N_SCR - 1) % gcra_engine::N_SCR);
+        if (overlap && is_prev) continue;
+        CK(cudaStreamWaitEvent(ms, os.ev_back, 0));
+    }
+    if (ip) {
+        RC(enqueue_mid_index(h, sc, h->scr[kn], v, compact, now_batch, overlap, ms, false));
+        CK(cudaEventRecord(sc.ev_mid, ms));
+        sc.mid_recorded = true;
+        cudaStream_t ts = h->tail_stream;
+        CK(cudaStreamWaitEvent(ts, sc.ev_mid, 0));
+        RC(enqueue_tail_index(h, sc, v, ts, false));
+        CK(cudaEventRecord(sc.ev_back, ts));
+        sc.back_recorded = true;
+        h->pend_set = (int)kn;
+        if (done) *done = sc.ev_back;
+        return snapshot_async(h, n_rows, ts);
+    }
+    RC(enqueue_back_sorted(h, sc, v, sorted, ms, false));
+    CK(cudaEventRecord(sc.ev_back, ms));
     sc.back_recorded = true;
+    h->pend_set = -1;
     if (done) *done = sc.ev_back;
-    return snapshot_async(h, n, h->back_stream);
+    return snapshot_async(h, n_rows, ms);
+}
+
+static int launch_pipelined(gcra_engine *h, uint32_t n, const void *d_req, bool compact, int64_t now_batch,
+                            gcra_result *d_res, cudaEvent_t ready, cudaEvent_t *done) {
+    if (n == 0) { if (done) *done = nullptr; return GCRA_OK; }
+    return launch_pipelined_view(h, single_view(d_req, d_res, n), n, compact, now_batch, ready, done);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -614,6 +846,7 @@ int32_t gcra_create(const gcra_config *cfg, gcra_engine **out) {
     cudaStreamCreateWithFlags(&h->front_stream[0], cudaStreamNonBlocking);
     for (int k = 1; k < gcra_engine::N_SCR; k++) h->front_stream[k] = h->front_stream[0];
     cudaStreamCreateWithFlags(&h->back_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&h->tail_stream, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming);
     h->capacity = cfg->capacity ? cfg->capacity : 1000;      // DEFAULT_CAPACITY adaptive_cleanup.rs:10
     h->max_batch = cfg->max_batch ? cfg->max_batch : (1u << 20);
@@ -628,6 +861,26 @@ int32_t gcra_create(const gcra_config *cfg, gcra_engine **out) {
     }
     const size_t mb = h->max_batch;
     const uint32_t stiles = (uint32_t)((mb + SORT_TILE - 1) / SORT_TILE);
+    {
+        // index-order pipeline: batch bitmap of 4-bit entries, 16 entries per row of the largest batch
+        // (a slot shares its entry with another slot of the batch with probability ~1/16), 64 K .. 64 M entries
+        uint32_t lg = ceil_log2(std::max<uint64_t>(16ULL * mb, 1ULL << 16));
+        if (lg > 26) lg = 26;
+        h->bm_mask = (1u << lg) - 1;
+        h->bm_words = (size_t)1 << (lg - 3);      // 4-bit entries, 8 per word
+        h->index_min = 32768;
+        if (const char *g = getenv("GCRA_INDEX_MIN")) h->index_min = (uint32_t)atoll(g);
+        if (cfg->flags & GCRA_FLAG_INDEX_PATH) h->index_min = SMALL_MAX + 1;
+        if (cfg->flags & GCRA_FLAG_SORT_PATH) h->index_min = 0;
+        h->prefetch_state = 0;
+        if (const char *g = getenv("GCRA_PREFETCH")) h->prefetch_state = atoi(g);
+        int sms = 148, nb = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, probe_kernel<false>, TILE_THREADS, 0) == cudaSuccess && nb > 0) h->grid_probe[0] = (uint32_t)(nb * sms);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, probe_kernel<true>, TILE_THREADS, 0) == cudaSuccess && nb > 0) h->grid_probe[1] = (uint32_t)(nb * sms);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decide_index_kernel<false>, TILE_THREADS, 0) == cudaSuccess && nb > 0) h->grid_decide[0] = (uint32_t)(nb * sms);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decide_index_kernel<true>, TILE_THREADS, 0) == cudaSuccess && nb > 0) h->grid_decide[1] = (uint32_t)(nb * sms);
+    }
     bool ok = cudaMalloc(&h->d_req, mb * sizeof(gcra_request)) == cudaSuccess &&
               cudaMalloc(&h->d_res, mb * sizeof(gcra_result)) == cudaSuccess &&
               cudaMalloc(&h->route_counts, (size_t)ROUTE_MAX_SHARDS * ((mb + TILE_THREADS - 1) / TILE_THREADS) * sizeof(u32)) == cudaSuccess &&
@@ -647,14 +900,17 @@ int32_t gcra_create(const gcra_config *cfg, gcra_engine **out) {
              cudaMalloc(&sc.long_count, 2 * sizeof(u32)) == cudaSuccess &&
              cudaEventCreateWithFlags(&sc.ev_front, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&sc.ev_back, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&sc.ev_mid, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&sc.ev_fork, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&sc.ev_join, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && alloc_index_scratch(h, sc, h->max_batch) == GCRA_OK;
     }
     if (!ok) return fail("scratch allocation", cudaGetLastError());
     memset(h->h_counters, 0, C_COUNT * sizeof(u64));
     cudaEventCreateWithFlags(&h->ev_counters, cudaEventDisableTiming);
     for (int i = 0; i < gcra_engine::N_SNAP; i++) cudaEventCreateWithFlags(&h->ev_snap[i], cudaEventDisableTiming);
     for (int i = 0; i < 4; i++) cudaEventCreate(&h->ev[i]);
+    for (int i = 0; i < 8; i++) cudaEventCreate(&h->evd[i]);
     cudaEventCreate(&h->ev_sweep[0]);
     cudaEventCreate(&h->ev_sweep[1]);
     // store policy, defaults as in the reference constructors
@@ -696,21 +952,24 @@ void gcra_destroy(gcra_engine *h) {
         cudaFreeHost(s.h_req); cudaFreeHost(s.h_res); cudaFree(s.d_req); cudaFree(s.d_res);
         cudaEventDestroy(s.ev_in); cudaEventDestroy(s.ev_comp); cudaEventDestroy(s.ev_done);
     }
-    cudaFree(h->tab.keys); cudaFree(h->tab.state); cudaFree(h->tab.ei); cudaFree(h->tab.counters);
+    cudaFree(h->tab.keys); cudaFree(h->tab.state); cudaFree(h->tab.ei); cudaFree(h->tab.mark); cudaFree(h->tab.counters);
     for (auto &sc : h->scr) {
         cudaFree(sc.drec); cudaFree(sc.keys_a); cudaFree(sc.keys_b); cudaFree(sc.hist); cudaFree(sc.tot);
         cudaFree(sc.long_runs); cudaFree(sc.giant_runs); cudaFree(sc.long_count);
-        cudaEventDestroy(sc.ev_front); cudaEventDestroy(sc.ev_back); cudaEventDestroy(sc.ev_fork); cudaEventDestroy(sc.ev_join);
+        cudaFree(sc.slot_arr); cudaFree(sc.flags); cudaFree(sc.bitmap); cudaFree(sc.ctrl_block); cudaFree(sc.ridx);
+        cudaFreeHost(sc.h_nres);
+        cudaEventDestroy(sc.ev_front); cudaEventDestroy(sc.ev_mid); cudaEventDestroy(sc.ev_back); cudaEventDestroy(sc.ev_fork); cudaEventDestroy(sc.ev_join);
     }
     cudaFree(h->d_req); cudaFree(h->d_res); cudaFree(h->route_counts); cudaFree(h->d_pol); cudaFree(h->d_op);
     cudaFreeHost(h->h_op); cudaFreeHost(h->h_counters); cudaFreeHost(h->h_snap);
     for (int i = 0; i < gcra_engine::N_SNAP; i++) cudaEventDestroy(h->ev_snap[i]);
     cudaEventDestroy(h->ev_counters);
     for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < 8; i++) cudaEventDestroy(h->evd[i]);
     cudaEventDestroy(h->ev_sweep[0]); cudaEventDestroy(h->ev_sweep[1]);
     cudaStreamDestroy(h->stream); cudaStreamDestroy(h->in_stream); cudaStreamDestroy(h->out_stream); cudaStreamDestroy(h->aux_stream);
     cudaStreamDestroy(h->front_stream[0]);
-    cudaStreamDestroy(h->back_stream); cudaEventDestroy(h->ev_ready);
+    cudaStreamDestroy(h->back_stream); cudaStreamDestroy(h->tail_stream); cudaEventDestroy(h->ev_ready);
     delete h;
 }
 
@@ -829,9 +1088,11 @@ int32_t gcra_rate_limit_batch_device_pipelined(gcra_engine *h, uint64_t n, const
 
 int32_t gcra_pipeline_join(gcra_engine *h, void *stream) {
     CK(cudaSetDevice(h->device));
-    CK(cudaEventRecord(h->ev_ready, h->back_stream));
-    if (stream) CK(cudaStreamWaitEvent((cudaStream_t)stream, h->ev_ready, 0));
-    else CK(cudaEventSynchronize(h->ev_ready));
+    for (auto &o : h->scr) {
+        if (!o.back_recorded) continue;
+        if (stream) CK(cudaStreamWaitEvent((cudaStream_t)stream, o.ev_back, 0));
+        else CK(cudaEventSynchronize(o.ev_back));
+    }
     return GCRA_OK;
 }
 
@@ -994,6 +1255,10 @@ int32_t gcra_get_stats(gcra_engine *h, gcra_stats *out) {
     out->swept = c[C_SWEPT];
     out->grows = h->n_grows;
     out->purges = h->n_purges;
+    out->index_batches = h->n_index_batches;
+    out->residue_rows = h->residue_seen;
+    out->residue_batches = h->residue_batches_seen;
+    out->drains = h->n_drains;
     return GCRA_OK;
 }
 
@@ -1010,6 +1275,7 @@ int32_t gcra_sync(gcra_engine *h) {
     CK(cudaStreamSynchronize(h->in_stream));
     CK(cudaStreamSynchronize(h->front_stream[0]));
     CK(cudaStreamSynchronize(h->back_stream));
+    CK(cudaStreamSynchronize(h->tail_stream));
     CK(cudaStreamSynchronize(h->aux_stream));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaStreamSynchronize(h->out_stream));
@@ -1025,6 +1291,15 @@ int32_t gcra_last_kernel_ms(gcra_engine *h, float out[4]) {
     CK(cudaEventElapsedTime(&out[3], h->ev[2], h->ev[3]));
     return GCRA_OK;
 }
+
+int32_t gcra_last_kernel_ms_detail(gcra_engine *h, float out[7]) {
+    if (!h->evd_valid) { h->err = "no timed index-order batch yet"; return GCRA_INTERNAL; }
+    CK(cudaEventSynchronize(h->evd[7]));
+    for (int i = 0; i < 7; i++) CK(cudaEventElapsedTime(&out[i], h->evd[i], h->evd[i + 1]));
+    return GCRA_OK;
+}
+
+void gcra_debug_set(gcra_engine *h, uint32_t mask) { h->dbg = mask; }
 
 int32_t gcra_last_sweep_ms(gcra_engine *h, float *ms) {
     if (!h->sweep_timed) { h->err = "no sweep yet"; return GCRA_INTERNAL; }
@@ -1108,7 +1383,7 @@ int32_t gcra_snapshot_load(gcra_engine *h, const char *path) {
         rc = alloc_table(h, hd.capacity, nt, nl, h->tab.counters);
         if (rc) { fclose(f); return rc; }
         CK(cudaStreamSynchronize(h->stream));
-        cudaFree(h->tab.keys); cudaFree(h->tab.state); cudaFree(h->tab.ei);
+        cudaFree(h->tab.keys); cudaFree(h->tab.state); cudaFree(h->tab.ei); cudaFree(h->tab.mark);
         h->tab = nt; h->total_lines = nl; h->capacity = hd.capacity;
     }
     std::vector<char> buf(SNAP_CHUNK);

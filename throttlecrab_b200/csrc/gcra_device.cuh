@@ -50,6 +50,7 @@ struct Table {
     u64 *keys;        // [slots]   main buckets (nb_main * 4 slots) followed by the stash slots
     TatOff *state;    // [slots]
     i64 *ei;          // [slots]
+    u64 *mark;        // [slots]  index-order pipeline: (~batch epoch << 32 | first state-changing row) of the slot
     u32 nb_main;      // buckets addressed by the two hash choices
     u32 stash_slots;  // slots probed linearly when both buckets are full
     u32 null_slot;    // reserved id: "this request has no slot" (last slot of the allocation)
@@ -128,9 +129,31 @@ struct Decision {
     bool live;     // stored entry visible to Store::get (adaptive_cleanup.rs:248)
 };
 
+// No operation of a decision can saturate or wrap when the clock, the parameters and the stored TAT are
+// "ordinary": 0 <= now < 2^61, 0 <= ei, dvt < 2^60, 0 <= q, ei * q < 2^60 and |tat| < 2^61 keep every
+// intermediate below 2^63 in magnitude, so the saturating forms equal plain two's-complement arithmetic there.
+__device__ __forceinline__ bool ordinary_request(const Req &r, i64 *inc) {
+    const u64 hi = __umul64hi((u64)r.ei, (u64)r.q);
+    const u64 lo = (u64)r.ei * (u64)r.q;
+    *inc = (i64)lo;
+    return (((u64)r.now >> 61) | ((u64)r.ei >> 60) | ((u64)r.dvt >> 60) | ((u64)r.q >> 60) | hi | (lo >> 60)) == 0;
+}
+
 __device__ __forceinline__ Decision decide(i64 s_tat, i64 s_exp, const Req &r) {
     Decision d;
     d.live = s_exp > r.now;
+    i64 inc;
+    if (ordinary_request(r, &inc) && (!d.live || (s_tat > -(1LL << 61) && s_tat < (1LL << 61)))) {
+        // fast path: the same sequence (rate_limiter.rs:158-183) in plain 64-bit arithmetic
+        d.tat = d.live ? max(s_tat, r.now - r.dvt) : r.now - r.ei;
+        d.new_tat = d.tat + inc;
+        d.allow_at = d.new_tat - r.dvt;
+        d.allowed = r.now >= d.allow_at;
+        const u64 ttl = (u64)((d.new_tat - r.now) + r.dvt);          // negative wraps (:179-183)
+        const u64 e = (u64)r.now + ttl;
+        d.new_exp = (e < ttl || e > (u64)I64_MAX) ? I64_MAX : (i64)e;
+        return d;
+    }
     d.tat = d.live ? max(s_tat, sat_sub(r.now, r.dvt)) : sat_sub(r.now, r.ei);
     d.new_tat = sat_add(d.tat, sat_mul(r.ei, r.q));
     d.allow_at = sat_sub(d.new_tat, r.dvt);
@@ -147,7 +170,9 @@ struct Outputs { i64 remaining, reset_after, retry_after; };
 __device__ __forceinline__ Outputs outputs_of(const Decision &d, const Req &r) {
     Outputs o;
     i64 cur = d.allowed ? d.new_tat : d.tat;
-    i64 room = sat_sub(wrap_add(r.now, r.dvt), cur);
+    // ordinary magnitudes (see ordinary_request; cur is then within +-2^62): nothing below saturates
+    const bool plain = ((((u64)r.now >> 61) | ((u64)r.dvt >> 60)) == 0) && cur > -(1LL << 62) && cur < (1LL << 62);
+    i64 room = plain ? (r.now + r.dvt) - cur : sat_sub(wrap_add(r.now, r.dvt), cur);
     // remaining = max(room / ei, 0) for ei > 0 (truncating).  room <= 0 gives 0.  Both operands below 2^53
     // (always, away from saturation corners): one IEEE double division, exact after a +-1 correction;
     // otherwise the 64-bit integer division.
@@ -163,10 +188,14 @@ __device__ __forceinline__ Outputs outputs_of(const Decision &d, const Req &r) {
         }
     }
     o.remaining = rem;
-    i64 reset = sat_add(sat_sub(cur, r.now), r.dvt);
+    i64 reset = plain ? (cur - r.now) + r.dvt : sat_add(sat_sub(cur, r.now), r.dvt);
     o.reset_after = reset < 0 ? 0 : reset;
     i64 retry = 0;
-    if (!d.allowed) { retry = sat_sub(d.allow_at, r.now); if (retry < 0) retry = 0; }
+    if (!d.allowed) {
+        // allow_at = new_tat - dvt stays within +-2^63 on the plain path (|new_tat| < 2^62 + 2^60)
+        retry = (plain && d.allow_at > -(1LL << 62) && d.allow_at < (1LL << 62)) ? d.allow_at - r.now : sat_sub(d.allow_at, r.now);
+        if (retry < 0) retry = 0;
+    }
     o.retry_after = retry;
     return o;
 }
@@ -227,13 +256,37 @@ __device__ __forceinline__ bool claim_in_bucket(const Table &t, u32 b, u64 kk[4]
     return false;
 }
 
+// Both bucket sectors of a key through L1.  Slots only fill while a kernel runs (nothing empties them), so a
+// key SEEN in a possibly stale L1 line is really there; a key not seen proves nothing and the caller goes on with
+// L2-coherent loads.  This keeps the hottest keys of a batch (thousands of requests on ONE sector) out of L2:
+// an LTS slice serves requests to one sector one after another.
+__device__ __forceinline__ u32 find_in_buckets_cached(const Table &t, u64 k, u32 b1, u32 b2) {
+    const ulonglong2 *p1 = reinterpret_cast<const ulonglong2 *>(t.keys + (size_t)b1 * 4);
+    const ulonglong2 a = p1[0], b = p1[1];
+    if (a.x == k) return b1 * 4;
+    if (a.y == k) return b1 * 4 + 1;
+    if (b.x == k) return b1 * 4 + 2;
+    if (b.y == k) return b1 * 4 + 3;
+    return t.null_slot;
+}
+
 // Lookup, claiming a slot when the key is absent.  Placement rule: first empty slot of bucket 1,
 // else of bucket 2, else the stash.  The rule only depends on state that is monotone during a
 // kernel (slots fill, never empty), so concurrent claimers of the SAME key always agree on one slot.
+__device__ __forceinline__ u32 find_or_claim_coherent(const Table &t, u64 k, u32 b1, u32 b2, bool &fresh);
+
 __device__ __forceinline__ u32 find_or_claim(const Table &t, u64 k, bool &fresh) {
     fresh = false;
     u32 b1, b2;
     bucket_choices(t, k, b1, b2);
+    const u32 hit = find_in_buckets_cached(t, k, b1, b2);
+    if (hit != t.null_slot) return hit;
+    return find_or_claim_coherent(t, k, b1, b2, fresh);
+}
+
+// the L2-coherent lookup / claim (everything find_or_claim does after the cached look at bucket 1)
+__device__ __forceinline__ u32 find_or_claim_coherent(const Table &t, u64 k, u32 b1, u32 b2, bool &fresh) {
+    fresh = false;
     u64 k1[4], k2[4];
     load_keys(t.keys + (size_t)b1 * 4, k1);
 #pragma unroll

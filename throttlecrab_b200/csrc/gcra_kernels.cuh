@@ -71,9 +71,51 @@ __device__ __forceinline__ void write_result(gcra_result *out, i64 remaining, i6
     reinterpret_cast<longlong2 *>(out)[1] = b;
 }
 
-// validation (rate_limiter.rs:111-117), parameter derivation, key probe/claim for ONE request whose record
-// sits at `rec` (shared or global memory).  Writes the derived request, the error result if any, and returns
-// the sort key (slot << 32 | i).  Must be called by all 32 lanes of a warp (warp-aggregated counters).
+// validation (rate_limiter.rs:111-117) + parameter derivation of ONE request record (shared or global memory):
+// returns the status the reference would return before touching the store, fills the key hash and the
+// derived request.
+template <bool COMPACT>
+__device__ __forceinline__ int parse_request(const unsigned char *rec, const PolicyDerived *__restrict__ pol, u32 npol,
+                                             i64 now_batch, u64 &key_hash, Req &r) {
+    int status = 0;
+    if (COMPACT) {
+        ulonglong2 w = *reinterpret_cast<const ulonglong2 *>(rec);
+        key_hash = w.x;
+        int qty = (int)(u32)(w.y & 0xffffffffULL);
+        u32 p = (u32)(w.y >> 32);
+        r.q = qty;
+        r.now = now_batch;
+        r.ei = 0;
+        r.dvt = 0;
+        if (qty < 0) status = GCRA_NEGATIVE_QUANTITY;          // rate_limiter.rs:111-113
+        else if (p >= npol) status = GCRA_INTERNAL;
+        else {
+            PolicyDerived pd = pol[p];
+            status = pd.status;
+            r.ei = pd.ei;
+            r.dvt = pd.dvt;
+        }
+    } else {
+        const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(rec);
+        ulonglong2 w0 = q[0], w1 = q[1], w2 = q[2];
+        key_hash = w0.x;
+        i64 max_burst = (i64)w0.y, count = (i64)w1.x, period = (i64)w1.y;
+        r.q = (i64)w2.x;
+        r.now = (i64)w2.y;
+        r.ei = 0;
+        r.dvt = 0;
+        if (r.q < 0) status = GCRA_NEGATIVE_QUANTITY;          // :111-113
+        else if (max_burst <= 0 || count <= 0 || period <= 0) status = GCRA_INVALID_RATE_LIMIT;  // :115-117
+        else status = derive_params(max_burst, count, period, &r.ei, &r.dvt);
+    }
+    // a pre-epoch `now` makes the reference read the wall clock (:128-143): not reproducible
+    if (status == 0 && r.now < 0) status = GCRA_INTERNAL;
+    return status;
+}
+
+// validation, parameter derivation, key probe/claim for ONE request whose record sits at `rec` (shared or
+// global memory).  Writes the derived request, the error result if any, and returns the sort key
+// (slot << 32 | i).  Must be called by all 32 lanes of a warp (warp-aggregated counters).
 template <bool COMPACT>
 __device__ __forceinline__ u64 ingest_one(const Table &t, const unsigned char *rec, bool in_range,
                                           const PolicyDerived *__restrict__ pol, u32 npol, i64 now_batch, u32 i,
@@ -81,36 +123,7 @@ __device__ __forceinline__ u64 ingest_one(const Table &t, const unsigned char *r
     int status = 0;
     u64 key_hash = 0;
     Req r = {0, 0, 0, 0};
-    if (in_range) {
-        if (COMPACT) {
-            ulonglong2 w = *reinterpret_cast<const ulonglong2 *>(rec);
-            key_hash = w.x;
-            int qty = (int)(u32)(w.y & 0xffffffffULL);
-            u32 p = (u32)(w.y >> 32);
-            r.q = qty;
-            r.now = now_batch;
-            if (qty < 0) status = GCRA_NEGATIVE_QUANTITY;          // rate_limiter.rs:111-113
-            else if (p >= npol) status = GCRA_INTERNAL;
-            else {
-                PolicyDerived pd = pol[p];
-                status = pd.status;
-                r.ei = pd.ei;
-                r.dvt = pd.dvt;
-            }
-        } else {
-            const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(rec);
-            ulonglong2 w0 = q[0], w1 = q[1], w2 = q[2];
-            key_hash = w0.x;
-            i64 max_burst = (i64)w0.y, count = (i64)w1.x, period = (i64)w1.y;
-            r.q = (i64)w2.x;
-            r.now = (i64)w2.y;
-            if (r.q < 0) status = GCRA_NEGATIVE_QUANTITY;          // :111-113
-            else if (max_burst <= 0 || count <= 0 || period <= 0) status = GCRA_INVALID_RATE_LIMIT;  // :115-117
-            else status = derive_params(max_burst, count, period, &r.ei, &r.dvt);
-        }
-        // a pre-epoch `now` makes the reference read the wall clock (:128-143): not reproducible
-        if (status == 0 && r.now < 0) status = GCRA_INTERNAL;
-    }
+    if (in_range) status = parse_request<COMPACT>(rec, pol, npol, now_batch, key_hash, r);
     u32 slot = t.null_slot;
     bool fresh = false;
     if (in_range && status == 0) {
@@ -198,92 +211,197 @@ __device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32 *part, u32 *total
     return before + inc - v;
 }
 
-__global__ void __launch_bounds__(TILE_THREADS)
-sort_hist_kernel(const u64 *__restrict__ in, u32 n, u32 shift, u32 bits, u32 num_tiles,
-                 u32 *__restrict__ hist) {
-    __shared__ u32 h[SORT_MAX_DIGITS];
+// All three kernels loop over the tiles (grid-stride), and take the element count either from the host
+// (`n`) or -- when `n_dev` is given -- from device memory: the residue of the index-order pipeline is only
+// known on the device, its kernels are launched with a fixed grid.
+__device__ __forceinline__ u32 sort_count(u32 n, const u32 *__restrict__ n_dev) { return n_dev ? *n_dev : n; }
+
+// the three phases of one pass; hist / tot are read through L2 (__ldcg): the fused kernel below reads what
+// OTHER CTAs of the same launch wrote a phase earlier
+__device__ __forceinline__ void sort_hist_body(u32 *h, const u64 *__restrict__ in, u32 n, u32 shift, u32 bits,
+                                               u32 *__restrict__ hist) {
+    const u32 num_tiles = (n + SORT_TILE - 1) / SORT_TILE;
     const u32 nd = 1u << bits, mask = nd - 1;
-    for (u32 d = threadIdx.x; d < nd; d += TILE_THREADS) h[d] = 0;
-    __syncthreads();
-    const u32 base = blockIdx.x * SORT_TILE;
+    for (u32 tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (u32 d = threadIdx.x; d < nd; d += TILE_THREADS) h[d] = 0;
+        __syncthreads();
+        const u32 base = tile * SORT_TILE;
 #pragma unroll
-    for (int k = 0; k < SORT_ITEMS; k++) {
-        u32 i = base + k * TILE_THREADS + threadIdx.x;
-        if (i < n) atomicAdd(&h[(u32)(in[i] >> shift) & mask], 1u);
+        for (int k = 0; k < SORT_ITEMS; k++) {
+            u32 i = base + k * TILE_THREADS + threadIdx.x;
+            if (i < n) atomicAdd(&h[(u32)(in[i] >> shift) & mask], 1u);
+        }
+        __syncthreads();
+        for (u32 d = threadIdx.x; d < nd; d += TILE_THREADS) hist[(size_t)d * num_tiles + tile] = h[d];
+        __syncthreads();
     }
-    __syncthreads();
-    for (u32 d = threadIdx.x; d < nd; d += TILE_THREADS) hist[(size_t)d * num_tiles + blockIdx.x] = h[d];
 }
 
-// one CTA per digit: exclusive scan of that digit's per-tile counts, digit total to tot[d]
-__global__ void __launch_bounds__(TILE_THREADS)
-sort_rowscan_kernel(u32 *__restrict__ hist, u32 num_tiles, u32 *__restrict__ tot) {
-    __shared__ u32 part[TILE_THREADS / 32];
-    u32 *row = hist + (size_t)blockIdx.x * num_tiles;
+// exclusive scan of digit `digit`'s per-tile counts, digit total to tot[digit] (the whole CTA works on it)
+__device__ __forceinline__ void sort_rowscan_body(u32 *part, u32 *__restrict__ hist, u32 n, u32 digit, u32 *__restrict__ tot) {
+    const u32 num_tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    u32 *row = hist + (size_t)digit * num_tiles;
     const u32 per = (num_tiles + TILE_THREADS - 1) / TILE_THREADS;
     const u32 lo = min(threadIdx.x * per, num_tiles), hi = min(lo + per, num_tiles);
     u32 s = 0;
-    for (u32 i = lo; i < hi; i++) s += row[i];
+    for (u32 i = lo; i < hi; i++) s += __ldcg(&row[i]);
     u32 total;
     u32 acc = block_exclusive_scan(s, part, &total);
-    for (u32 i = lo; i < hi; i++) { u32 v = row[i]; row[i] = acc; acc += v; }
-    if (threadIdx.x == 0) tot[blockIdx.x] = total;
+    for (u32 i = lo; i < hi; i++) { u32 v = __ldcg(&row[i]); row[i] = acc; acc += v; }
+    if (threadIdx.x == 0) tot[digit] = total;
+    __syncthreads();   // `part` is reused by the next call
+}
+
+struct SortScatterSmem {
+    u32 cnt[TILE_THREADS / 32][SORT_MAX_DIGITS];   // per-warp digit counters -> per-warp offsets
+    u32 gbase[SORT_MAX_DIGITS];                    // global base of (digit, this tile)
+    u32 part[TILE_THREADS / 32];
+};
+
+__device__ __forceinline__ void sort_scatter_body(SortScatterSmem &sm, const u64 *__restrict__ in, u64 *__restrict__ outk,
+                                                  u32 n, u32 shift, u32 bits, const u32 *__restrict__ hist,
+                                                  const u32 *__restrict__ tot) {
+    constexpr int NW = TILE_THREADS / 32;
+    const u32 num_tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    if (blockIdx.x >= num_tiles) return;       // uniform over the CTA
+    const u32 nd = 1u << bits, mask = nd - 1;
+    const u32 w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // exclusive scan of the digit totals (nd <= 512: two consecutive digits per thread), once per CTA
+    const u32 d0 = 2 * threadIdx.x, d1 = d0 + 1;
+    const u32 t0 = d0 < nd ? __ldcg(&tot[d0]) : 0, t1 = d1 < nd ? __ldcg(&tot[d1]) : 0;
+    u32 total;
+    const u32 ex = block_exclusive_scan(t0 + t1, sm.part, &total);
+    const u32 lt = (1u << lane) - 1;
+    for (u32 tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (u32 d = threadIdx.x; d < nd; d += TILE_THREADS) {
+#pragma unroll
+            for (int x = 0; x < NW; x++) sm.cnt[x][d] = 0;
+        }
+        if (d0 < nd) sm.gbase[d0] = ex + __ldcg(&hist[(size_t)d0 * num_tiles + tile]);
+        if (d1 < nd) sm.gbase[d1] = ex + t0 + __ldcg(&hist[(size_t)d1 * num_tiles + tile]);
+        __syncthreads();
+        // warp w owns tile elements [w*128, w*128+128): item k, lane l -> w*128 + k*32 + l (index order)
+        const u32 base = tile * SORT_TILE + w * (32 * SORT_ITEMS);
+        u64 key[SORT_ITEMS];
+        u32 dig[SORT_ITEMS], rank[SORT_ITEMS];
+#pragma unroll
+        for (int k = 0; k < SORT_ITEMS; k++) {
+            u32 i = base + k * 32 + lane;
+            bool valid = i < n;
+            key[k] = valid ? in[i] : 0;
+            dig[k] = (u32)(key[k] >> shift) & mask;
+            u32 peers = __match_any_sync(0xffffffffu, valid ? dig[k] : (0x80000000u | lane));
+            u32 before = valid ? sm.cnt[w][dig[k]] : 0;
+            rank[k] = before + __popc(peers & lt);
+            __syncwarp();
+            if (valid && (peers & lt) == 0) sm.cnt[w][dig[k]] = before + __popc(peers);
+            __syncwarp();
+        }
+        __syncthreads();
+        // per digit: exclusive scan over the warps
+        for (u32 d = threadIdx.x; d < nd; d += TILE_THREADS) {
+            u32 acc = 0;
+#pragma unroll
+            for (int x = 0; x < NW; x++) { u32 v = sm.cnt[x][d]; sm.cnt[x][d] = acc; acc += v; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < SORT_ITEMS; k++) {
+            u32 i = base + k * 32 + lane;
+            if (i < n) outk[sm.gbase[dig[k]] + sm.cnt[w][dig[k]] + rank[k]] = key[k];
+        }
+        __syncthreads();
+    }
 }
 
 __global__ void __launch_bounds__(TILE_THREADS)
-sort_scatter_kernel(const u64 *__restrict__ in, u64 *__restrict__ outk, u32 n, u32 shift, u32 bits,
-                    u32 num_tiles, const u32 *__restrict__ hist, const u32 *__restrict__ tot) {
-    constexpr int NW = TILE_THREADS / 32;
-    __shared__ u32 cnt[NW][SORT_MAX_DIGITS];   // per-warp digit counters -> per-warp offsets
-    __shared__ u32 gbase[SORT_MAX_DIGITS];     // global base of (digit, this tile)
-    const u32 nd = 1u << bits, mask = nd - 1;
-    const u32 w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    __shared__ u32 part[NW];
-    for (u32 d = threadIdx.x; d < nd; d += TILE_THREADS) {
-#pragma unroll
-        for (int x = 0; x < NW; x++) cnt[x][d] = 0;
-    }
-    {   // exclusive scan of the digit totals (nd <= 512: two consecutive digits per thread)
-        const u32 d0 = 2 * threadIdx.x, d1 = d0 + 1;
-        const u32 t0 = d0 < nd ? tot[d0] : 0, t1 = d1 < nd ? tot[d1] : 0;
-        u32 total;
-        const u32 ex = block_exclusive_scan(t0 + t1, part, &total);
-        if (d0 < nd) gbase[d0] = ex + hist[(size_t)d0 * num_tiles + blockIdx.x];
-        if (d1 < nd) gbase[d1] = ex + t0 + hist[(size_t)d1 * num_tiles + blockIdx.x];
-    }
-    __syncthreads();
-    // warp w owns tile elements [w*128, w*128+128): item k, lane l -> w*128 + k*32 + l (index order)
-    const u32 base = blockIdx.x * SORT_TILE + w * (32 * SORT_ITEMS);
-    u64 key[SORT_ITEMS];
-    u32 dig[SORT_ITEMS], rank[SORT_ITEMS];
-    const u32 lt = (1u << lane) - 1;
-#pragma unroll
-    for (int k = 0; k < SORT_ITEMS; k++) {
-        u32 i = base + k * 32 + lane;
-        bool valid = i < n;
-        key[k] = valid ? in[i] : 0;
-        dig[k] = (u32)(key[k] >> shift) & mask;
-        u32 peers = __match_any_sync(0xffffffffu, valid ? dig[k] : (0x80000000u | lane));
-        u32 before = valid ? cnt[w][dig[k]] : 0;
-        rank[k] = before + __popc(peers & lt);
-        __syncwarp();
-        if (valid && (peers & lt) == 0) cnt[w][dig[k]] = before + __popc(peers);
-        __syncwarp();
-    }
-    __syncthreads();
-    // per digit: exclusive scan over the warps
-    for (u32 d = threadIdx.x; d < nd; d += TILE_THREADS) {
-        u32 acc = 0;
-#pragma unroll
-        for (int x = 0; x < NW; x++) { u32 v = cnt[x][d]; cnt[x][d] = acc; acc += v; }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < SORT_ITEMS; k++) {
-        u32 i = base + k * 32 + lane;
-        if (i < n) outk[gbase[dig[k]] + cnt[w][dig[k]] + rank[k]] = key[k];
-    }
+sort_hist_kernel(const u64 *__restrict__ in, u32 n_host, const u32 *__restrict__ n_dev, u32 shift, u32 bits,
+                 u32 *__restrict__ hist) {
+    __shared__ u32 h[SORT_MAX_DIGITS];
+    sort_hist_body(h, in, sort_count(n_host, n_dev), shift, bits, hist);
 }
+
+// one CTA per digit
+__global__ void __launch_bounds__(TILE_THREADS)
+sort_rowscan_kernel(u32 *__restrict__ hist, u32 n_host, const u32 *__restrict__ n_dev, u32 *__restrict__ tot) {
+    __shared__ u32 part[TILE_THREADS / 32];
+    sort_rowscan_body(part, hist, sort_count(n_host, n_dev), blockIdx.x, tot);
+}
+
+__global__ void __launch_bounds__(TILE_THREADS)
+sort_scatter_kernel(const u64 *__restrict__ in, u64 *__restrict__ outk, u32 n_host, const u32 *__restrict__ n_dev,
+                    u32 shift, u32 bits, const u32 *__restrict__ hist, const u32 *__restrict__ tot) {
+    __shared__ SortScatterSmem sm;
+    sort_scatter_body(sm, in, outk, sort_count(n_host, n_dev), shift, bits, hist, tot);
+}
+
+// One radix pass in ONE launch for small inputs (the residue of the index-order pipeline: its nine launches of a
+// few microseconds each were pure launch latency).  All CTAs are resident (the host launches at most what fits),
+// the phases are separated by a grid-wide barrier on a counter that the host zeroes once per batch: the barrier
+// after phase p of pass q is complete when the counter reaches (2 q + p + 1) * gridDim.x.
+__device__ __forceinline__ void grid_barrier(u32 *cnt, u32 target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(cnt, 1u);
+        while (*reinterpret_cast<volatile u32 *>(cnt) < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(TILE_THREADS)
+sort_pass_fused_kernel(const u64 *__restrict__ in, u64 *__restrict__ outk, const u32 *__restrict__ n_dev, u32 shift,
+                       u32 bits, u32 *__restrict__ hist, u32 *__restrict__ tot, u32 *__restrict__ bar_cnt, u32 pass) {
+    __shared__ SortScatterSmem sm;
+    const u32 n = *n_dev;
+    if (n == 0) return;                                   // uniform over the grid: nobody enters a barrier
+    sort_hist_body(sm.gbase, in, n, shift, bits, hist);   // (gbase doubles as the histogram of phase 1)
+    grid_barrier(bar_cnt, (2 * pass + 1) * gridDim.x);
+    for (u32 d = blockIdx.x; d < (1u << bits); d += gridDim.x) sort_rowscan_body(sm.part, hist, n, d, tot);
+    grid_barrier(bar_cnt, (2 * pass + 2) * gridDim.x);
+    sort_scatter_body(sm, in, outk, n, shift, bits, hist, tot);
+}
+
+// ---------------------------------------------------------------------------------------------
+// A batch as the kernels see it: one segment of n rows (host-known count), or -- multi-GPU, rows written
+// by peer GPUs straight into this GPU's inbox -- up to MAX_SEGS segments whose row counts live in device
+// memory.  Row id = (segment << cap_shift) | row-in-segment; results of a row go to its segment's result
+// array (for a peer's segment that is a peer-mapped pointer: the result travels back over NVLink as it is
+// written).
+// ---------------------------------------------------------------------------------------------
+constexpr int MAX_SEGS = 16;
+struct SegDesc {
+    const unsigned char *req;
+    gcra_result *res;
+};
+struct BatchView {
+    const unsigned char *req0;   // nseg == 1
+    gcra_result *res0;
+    const SegDesc *segs;         // device array [nseg], nseg > 1
+    const u32 *dev_counts;       // device array [nseg], nseg > 1
+    u32 n;                       // nseg == 1: number of rows
+    u32 nseg;
+    u32 cap_shift;               // nseg > 1: log2 of the per-segment row capacity
+
+    __device__ __forceinline__ gcra_result *res_at(u32 i) const {
+        if (nseg == 1) return res0 + i;
+        return (gcra_result *)__ldg((const u64 *)&segs[i >> cap_shift].res) + (i & ((1u << cap_shift) - 1));
+    }
+    __device__ __forceinline__ const unsigned char *req_at(u32 i, u32 rsz) const {
+        if (nseg == 1) return req0 + (size_t)i * rsz;
+        return (const unsigned char *)__ldg((const u64 *)&segs[i >> cap_shift].req) + (size_t)(i & ((1u << cap_shift) - 1)) * rsz;
+    }
+};
+
+// where the result of sorted position `p` goes: the sort path numbers requests by batch index (out + p);
+// the residue of the index-order pipeline numbers them by residue position and keeps their row ids aside
+struct OutMap {
+    gcra_result *out;
+    const u32 *ridx;             // residue position -> row id (nullptr: identity)
+    BatchView view;
+    __device__ __forceinline__ gcra_result *at(u32 p) const { return ridx ? view.res_at(ridx[p]) : out + p; }
+};
 
 // ---------------------------------------------------------------------------------------------
 // K1c: decide -- the GCRA theoretical-arrival-time compare-and-update
@@ -398,7 +516,7 @@ constexpr int DECIDE_THREADS = GCRA_DECIDE_THREADS;   // warps are independent: 
 
 // one warp, one chunk of 32 sorted positions (see the comment above run_chunk)
 __device__ __forceinline__ void decide_chunk(const Table &t, const u64 *sorted, const Req *__restrict__ drec, u32 n,
-                                             gcra_result *__restrict__ out, LongRun *__restrict__ long_runs,
+                                             const OutMap &out, LongRun *__restrict__ long_runs,
                                              LongRun *__restrict__ giant_runs, u32 *__restrict__ long_count,
                                              u32 warp_global, u32 lane) {
     const u32 base = warp_global * 32;
@@ -473,7 +591,7 @@ __device__ __forceinline__ void decide_chunk(const Table &t, const u64 *sorted, 
     u32 n_allowed = 0, n_denied = 0;
     if (mine) {
         Outputs o = outputs_of(fin, r);
-        write_result(out + idx, o.remaining, o.reset_after, o.retry_after, 0, fin.allowed ? 1 : 0);
+        write_result(out.at(idx), o.remaining, o.reset_after, o.retry_after, 0, fin.allowed ? 1 : 0);
         n_allowed += fin.allowed ? 1 : 0;
         n_denied += fin.allowed ? 0 : 1;
     }
@@ -525,7 +643,7 @@ __device__ __forceinline__ void decide_chunk(const Table &t, const u64 *sorted, 
             run_chunk(lane, in_run, rm, r2, s2, f2, ch2, exp_hits);
             if (in_run) {
                 Outputs o = outputs_of(f2, r2);
-                write_result(out + (u32)e2, o.remaining, o.reset_after, o.retry_after, 0, f2.allowed ? 1 : 0);
+                write_result(out.at((u32)e2), o.remaining, o.reset_after, o.retry_after, 0, f2.allowed ? 1 : 0);
                 n_allowed += f2.allowed ? 1 : 0;
                 n_denied += f2.allowed ? 0 : 1;
             }
@@ -557,11 +675,13 @@ __device__ __forceinline__ void decide_chunk(const Table &t, const u64 *sorted, 
 }
 
 __global__ void __launch_bounds__(DECIDE_THREADS, 1024 / DECIDE_THREADS)
-decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ drec, u32 n,
-              gcra_result *__restrict__ out, LongRun *__restrict__ long_runs, LongRun *__restrict__ giant_runs,
-              u32 *__restrict__ long_count) {
-    decide_chunk(t, sorted, drec, n, out, long_runs, giant_runs, long_count,
-                 (blockIdx.x * DECIDE_THREADS + threadIdx.x) >> 5, threadIdx.x & 31);
+decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ drec, u32 n_host,
+              const u32 *__restrict__ n_dev, OutMap out, LongRun *__restrict__ long_runs,
+              LongRun *__restrict__ giant_runs, u32 *__restrict__ long_count) {
+    const u32 n = sort_count(n_host, n_dev);
+    const u32 warps_total = gridDim.x * (DECIDE_THREADS / 32);
+    for (u32 wg = (blockIdx.x * DECIDE_THREADS + threadIdx.x) >> 5; wg * 32 < n; wg += warps_total)
+        decide_chunk(t, sorted, drec, n, out, long_runs, giant_runs, long_count, wg, threadIdx.x & 31);
 }
 
 // Small batches (n < LONG_RUN_MIN, e.g. one RateLimiter::rate_limit call or a lightly loaded actor): ONE CTA
@@ -595,7 +715,10 @@ small_batch_kernel(Table t, const void *__restrict__ req_base, const PolicyDeriv
         }
     }
     __threadfence_block();   // drec / state written above are read below by other warps of this CTA
-    decide_chunk(t, keys, drec, n, out, nullptr, nullptr, nullptr, tid >> 5, tid & 31);
+    OutMap om;
+    om.out = out;
+    om.ridx = nullptr;
+    decide_chunk(t, keys, drec, n, om, nullptr, nullptr, nullptr, tid >> 5, tid & 31);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -655,7 +778,7 @@ struct PubState { i64 tat, exp; };
 template <int CTAS>
 __global__ void __launch_bounds__(LONG_THREADS, 1)
 decide_runs_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ drec,
-                   gcra_result *__restrict__ out, const LongRun *__restrict__ runs,
+                   OutMap out, const LongRun *__restrict__ runs,
                    const u32 *__restrict__ count_ptr) {
     namespace cg = cooperative_groups;
     constexpr int NW = LONG_THREADS / 32;
@@ -789,7 +912,7 @@ decide_runs_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restric
                     cd.get(in_idx, ct, ce);
                     const Decision d = decide(ct, ce, r);
                     const Outputs o = outputs_of(d, r);
-                    write_result(out + idx, o.remaining, o.reset_after, o.retry_after, 0, d.allowed ? 1 : 0);
+                    write_result(out.at(idx), o.remaining, o.reset_after, o.retry_after, 0, d.allowed ? 1 : 0);
                     n_allowed += d.allowed ? 1 : 0;
                     n_denied += d.allowed ? 0 : 1;
                     if (d.allowed && !d.live && ce >= 0) exp_hits++;
