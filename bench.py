@@ -256,6 +256,7 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = store.launch_count()
+    stats0 = store.stats()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k1_ms = []
     torch.cuda.synchronize()
@@ -470,8 +471,11 @@ def main():
                 "serial_tick_phase_ms": {"total": phases[0], "probe+note": phases[1], "decide+resolve": phases[2],
                                          "sorted_residue": phases[3]},
                 "serial_tick_detail_ms": phase_detail,
-                "residue_fraction": (st_k["residue_rows"] / max(st_k["residue_batches"], 1)) / TICK,
-                "pipeline_drains": st_k["drains"], "index_batches": st_k["index_batches"]}
+                # requests that went through the sorted tail, over the batches of the timed region whose count
+                # had reached the host when the last one was submitted
+                "residue_fraction": ((st_k["residue_rows"] - stats0["residue_rows"])
+                                     / max(st_k["residue_batches"] - stats0["residue_batches"], 1)) / TICK,
+                "pipeline_drains": st_k["drains"] - stats0["drains"], "index_batches": st_k["index_batches"]}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

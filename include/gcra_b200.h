@@ -105,6 +105,7 @@ typedef struct {
     /* index-order K1 pipeline: batches it carried; residue rows (requests that went through the sorted tail) summed
      * over the `residue_batches` batches whose count has reached the host; times stage 2 waited for every tail */
     uint64_t index_batches, residue_rows, residue_batches, drains;
+    uint64_t path_switches;   /* times the residue feedback sent the following batches to the sort pipeline */
 } gcra_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------- */

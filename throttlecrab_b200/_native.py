@@ -41,7 +41,7 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in
                 ("len", "occupied_slots", "table_slots", "stash_entries", "allowed", "denied",
                  "errors", "expired_hits", "sweeps", "swept", "grows", "purges",
-                 "index_batches", "residue_rows", "residue_batches", "drains")]
+                 "index_batches", "residue_rows", "residue_batches", "drains", "path_switches")]
 
 
 def sources():

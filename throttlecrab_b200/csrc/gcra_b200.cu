@@ -128,14 +128,14 @@ struct Scratch {
     u32 *hist = nullptr, *tot = nullptr;
     LongRun *long_runs = nullptr, *giant_runs = nullptr;
     u32 *long_count = nullptr;
-    cudaEvent_t ev_front = nullptr, ev_mid = nullptr, ev_back = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_front = nullptr, ev_mid = nullptr, ev_back = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
     bool back_recorded = false;
     // index-order pipeline (gcra_index_path.cuh)
     u32 *slot_arr = nullptr;            // [rows] slot of every row (null slot: the row failed validation)
     unsigned char *flags = nullptr;     // [rows] pass-B verdict of rows on shared slots
-    u32 *bitmap = nullptr;              // [bm_words] 2 bits per entry: seen / seen twice
+    u32 *bitmap = nullptr;              // [bm_words] 16-bit occurrence counters of the batch, hashed by slot
+    u32 *pend = nullptr;                // [pend_words] 1 bit per entry: the PREVIOUS batch's tail owns a slot of the entry
     u64 *ctrl_block = nullptr;          // word 0: {tile ticket, residue count}; word 1: {sort barrier, -}; then one status word per tile
-    u32 *ridx = nullptr;                // [rows] residue position -> row id
     uint32_t rows_alloc = 0;
     u32 *h_nres = nullptr;              // pinned: residue size of the set's latest index-order batch (valid after ev_mid)
     bool mid_recorded = false, nres_counted = true;
@@ -144,7 +144,7 @@ struct Scratch {
 
 struct gcra_engine {
     int device = 0;
-    cudaStream_t stream = nullptr, in_stream = nullptr, out_stream = nullptr, aux_stream = nullptr;
+    cudaStream_t stream = nullptr, in_stream = nullptr, out_stream = nullptr, aux_stream = nullptr, aux2_stream = nullptr;
     Table tab{};
     uint32_t total_lines = 0;
     uint64_t capacity = 0;
@@ -199,12 +199,16 @@ struct gcra_engine {
     // index-order pipeline
     uint32_t epoch = 0;              // batch epoch of the slot marks (never 0)
     uint32_t bm_mask = 0;            // bitmap entries - 1
-    size_t bm_words = 0;
+    size_t bm_words = 0, pend_words = 0;
     uint32_t index_min = 0;          // batches of at least this many rows take the index-order pipeline (0: never)
     int prefetch_state = 0;
     uint32_t max_tiles = 0;
     uint32_t grid_probe[2] = {592, 592}, grid_decide[2] = {444, 444};   // resident CTAs of the persistent kernels [compact]
     uint32_t dbg = 0;                // timing experiments only (gcra_debug_set): skips parts of pass B
+    uint32_t last_nres = 0, last_nres_rows = 0;   // newest residue size that has reached the host (and its batch's rows)
+    bool adaptive = true;            // choose the pipeline from the residue feedback (off when a test / env forces one)
+    uint64_t n_path_switches = 0;
+    uint32_t sort_hold = 0;          // > 0: the residue was large, this many more batches take the sort pipeline
     uint32_t since_drain = 0;        // index-order batches submitted since stage 2 last waited for every tail
     uint64_t n_drains = 0, n_index_batches = 0, residue_seen = 0, residue_batches_seen = 0;
     // ring
@@ -505,7 +509,12 @@ static int enqueue_sort(gcra_engine *h, Scratch &sc, uint32_t n_max, const u32 *
     const uint32_t bits = h->tab.slot_bits;
     const uint32_t passes = (bits + SORT_MAX_BITS - 1) / SORT_MAX_BITS;
     uint32_t stiles = (n_max + SORT_TILE - 1) / SORT_TILE;
-    if (n_dev) stiles = std::min<uint32_t>(stiles, 2 * 148);      // fixed grid, all CTAs resident: the kernels loop over the tiles
+    if (n_dev) {
+        // fixed grid, all CTAs resident (grid barriers), the kernels loop over the tiles: sized for about twice the
+        // residue the host saw last (a barrier over few CTAs is cheaper), any size is correct
+        const uint32_t guess = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(2ULL * h->last_nres, n_max / 8) + 8 * SORT_TILE, n_max);
+        stiles = std::max<uint32_t>(std::min<uint32_t>((guess + SORT_TILE - 1) / SORT_TILE, 2 * 148), 8);
+    }
     u64 *src = sc.keys_a, *dst = sc.keys_b;
     uint32_t shift = 32;
     for (uint32_t p = 0; p < passes; p++) {
@@ -536,7 +545,7 @@ static int enqueue_decide_sorted(gcra_engine *h, Scratch &sc, uint32_t n_max, co
     uint32_t grid = (warps + DECIDE_THREADS / 32 - 1) / (DECIDE_THREADS / 32);
     if (n_dev) grid = std::min<uint32_t>(grid, 4 * 148);
     decide_kernel<<<grid, DECIDE_THREADS, 0, st>>>(h->tab, src, sc.drec, n_max, n_dev, om, sc.long_runs, sc.giant_runs,
-                                                   sc.long_count);
+                                                   sc.long_count, 0);
     h->launches++;
     if (n_max >= GIANT_RUN_MIN) {
         // the two hot-run kernels work on disjoint runs: the one-CTA-per-run kernel goes to a side
@@ -557,24 +566,28 @@ static int enqueue_decide_sorted(gcra_engine *h, Scratch &sc, uint32_t n_max, co
 
 // per-set buffers of the index-order pipeline for batches of up to `rows` row ids
 static int alloc_index_scratch(gcra_engine *h, Scratch &sc, uint32_t rows) {
-    cudaFree(sc.slot_arr); cudaFree(sc.flags); cudaFree(sc.ridx); cudaFree(sc.ctrl_block);
-    sc.slot_arr = nullptr; sc.flags = nullptr; sc.ridx = nullptr; sc.ctrl_block = nullptr;
+    cudaFree(sc.slot_arr); cudaFree(sc.flags); cudaFree(sc.ctrl_block);
+    sc.slot_arr = nullptr; sc.flags = nullptr; sc.ctrl_block = nullptr;
     const uint32_t tiles = (rows + TILE_THREADS - 1) / TILE_THREADS;
     if (tiles > h->max_tiles) h->max_tiles = tiles;
     CK(cudaMalloc(&sc.slot_arr, (size_t)rows * sizeof(u32)));
     CK(cudaMalloc(&sc.flags, (size_t)rows));
-    CK(cudaMalloc(&sc.ridx, (size_t)h->max_batch * sizeof(u32)));
     CK(cudaMalloc(&sc.ctrl_block, ((size_t)h->max_tiles + 2) * sizeof(u64)));
     if (!sc.h_nres) { CK(cudaMallocHost(&sc.h_nres, sizeof(u32))); *sc.h_nres = 0; }
     if (!sc.bitmap) {
         CK(cudaMalloc(&sc.bitmap, h->bm_words * sizeof(u32)));
+        CK(cudaMalloc(&sc.pend, h->pend_words * sizeof(u32)));
         CK(cudaMemsetAsync(sc.bitmap, 0, h->bm_words * sizeof(u32), h->stream));   // from then on cleared after every use
+        CK(cudaMemsetAsync(sc.pend, 0, h->pend_words * sizeof(u32), h->stream));
     }
     sc.rows_alloc = rows;
     return GCRA_OK;
 }
 
-static bool use_index_path(const gcra_engine *h, uint32_t n) { return h->index_min != 0 && n >= h->index_min; }
+static bool use_index_path(const gcra_engine *h, uint32_t n) {
+    // (the batch counters hold at most 2 x tiles per entry in 16 bits: batches of 2^22 rows and more take the sort pipeline)
+    return h->index_min != 0 && n >= h->index_min && n < (1u << 22);
+}
 
 static uint32_t view_max_rows(const BatchView &v) { return v.nseg == 1 ? v.n : (v.nseg << v.cap_shift); }
 
@@ -593,13 +606,13 @@ static int enqueue_front(gcra_engine *h, Scratch &sc, const BatchView &v, bool i
         CK(cudaMemsetAsync(sc.ctrl_block, 0, ((size_t)h->max_tiles + 2) * sizeof(u64), st));
         if (timed) CK(cudaEventRecord(h->evd[0], st));
         if (compact)
-            probe_kernel<true><<<grid, TILE_THREADS, 0, st>>>(h->tab, v, h->d_pol, h->npol, now_batch, sc.slot_arr,
-                                                              h->prefetch_state);
+            probe_kernel<true><<<grid, TILE_THREADS, 0, st>>>(h->tab, v, h->d_pol, h->npol, now_batch, sc.slot_arr, sc.bitmap,
+                                                              h->bm_mask, h->prefetch_state);
         else
-            probe_kernel<false><<<grid, TILE_THREADS, 0, st>>>(h->tab, v, nullptr, 0, 0, sc.slot_arr, h->prefetch_state);
+            probe_kernel<false><<<grid, TILE_THREADS, 0, st>>>(h->tab, v, nullptr, 0, 0, sc.slot_arr, sc.bitmap, h->bm_mask,
+                                                               h->prefetch_state);
         if (timed) CK(cudaEventRecord(h->evd[1], st));
-        note_kernel<<<std::min<uint32_t>(tiles, 16 * 148), TILE_THREADS, 0, st>>>(v, h->tab.null_slot, sc.slot_arr, sc.bitmap, h->bm_mask);
-        h->launches += 2;
+        h->launches += 1;
         if (timed) { CK(cudaEventRecord(h->ev[1], st)); CK(cudaEventRecord(h->evd[2], st)); }
         return GCRA_OK;
     }
@@ -623,7 +636,7 @@ static int enqueue_front(gcra_engine *h, Scratch &sc, const BatchView &v, bool i
 // of this batch's residue keys in its bitmap.  This set's own bitmap is cleared for its next use afterwards.
 static int enqueue_mid_index(gcra_engine *h, Scratch &sc, Scratch &next, const BatchView &v, bool compact, int64_t now_batch,
                              bool honour_pend, cudaStream_t st, bool timed) {
-    const u32 pend_mask = honour_pend ? 0xFu : (0xFu & ~BM_PEND);
+    const u32 hp = honour_pend ? 1u : 0u;
     if (++h->epoch == 0) {
         // the 32-bit batch epoch wrapped: forget every mark (once per 4 G batches)
         CK(cudaMemsetAsync(h->tab.mark, 0xff, (size_t)h->total_lines * 4 * sizeof(u64), st));
@@ -636,22 +649,21 @@ static int enqueue_mid_index(gcra_engine *h, Scratch &sc, Scratch &next, const B
     u64 *status = sc.ctrl_block + 2;
     if (compact) {
         decide_index_kernel<true><<<grid, TILE_THREADS, 0, st>>>(h->tab, v, h->d_pol, h->npol, now_batch, sc.slot_arr,
-                                                                 sc.bitmap, h->bm_mask, sc.flags, h->epoch, pend_mask, h->dbg);
-        resolve_kernel<true><<<rgrid, TILE_THREADS, 0, st>>>(h->tab, v, h->d_pol, h->npol, now_batch, sc.slot_arr, sc.bitmap,
+                                                                 sc.bitmap, sc.pend, h->bm_mask, sc.flags, h->epoch, hp, h->dbg);
+        resolve_kernel<true><<<rgrid, TILE_THREADS, 0, st>>>(h->tab, v, h->d_pol, h->npol, now_batch, sc.slot_arr,
                                                              h->bm_mask, sc.flags, h->epoch, ctrl, status, sc.keys_a,
-                                                             sc.ridx, sc.drec, next.bitmap, pend_mask, sc.h_nres);
+                                                             next.pend, sc.h_nres);
     } else {
-        decide_index_kernel<false><<<grid, TILE_THREADS, 0, st>>>(h->tab, v, nullptr, 0, 0, sc.slot_arr, sc.bitmap,
-                                                                  h->bm_mask, sc.flags, h->epoch, pend_mask, h->dbg);
+        decide_index_kernel<false><<<grid, TILE_THREADS, 0, st>>>(h->tab, v, nullptr, 0, 0, sc.slot_arr, sc.bitmap, sc.pend,
+                                                                  h->bm_mask, sc.flags, h->epoch, hp, h->dbg);
         if (timed) CK(cudaEventRecord(h->evd[3], st));
-        resolve_kernel<false><<<rgrid, TILE_THREADS, 0, st>>>(h->tab, v, nullptr, 0, 0, sc.slot_arr, sc.bitmap, h->bm_mask,
-                                                              sc.flags, h->epoch, ctrl, status, sc.keys_a, sc.ridx,
-                                                              sc.drec, next.bitmap, pend_mask, sc.h_nres);
+        resolve_kernel<false><<<rgrid, TILE_THREADS, 0, st>>>(h->tab, v, nullptr, 0, 0, sc.slot_arr, h->bm_mask,
+                                                              sc.flags, h->epoch, ctrl, status, sc.keys_a,
+                                                              next.pend, sc.h_nres);
     }
     h->launches += 2;
     h->n_index_batches++;
     if (timed) CK(cudaEventRecord(h->evd[4], st));
-    CK(cudaMemsetAsync(sc.bitmap, 0, h->bm_words * sizeof(u32), st));
     // (pass C wrote the residue size of this batch to sc.h_nres, mapped pinned host memory: read, once ev_mid has
     // completed, when later batches are submitted)
     sc.nres_rows = std::min<uint32_t>(rows, h->max_batch);
@@ -664,17 +676,26 @@ static int enqueue_mid_index(gcra_engine *h, Scratch &sc, Scratch &next, const B
 // Stage 3 of an index-order batch: the residue (requests behind the first state change of their key, and
 // requests deferred because the previous batch's tail still owned their key) through the sort pipeline; its
 // size only exists on the device.  Tails run strictly in submission order.
-static int enqueue_tail_index(gcra_engine *h, Scratch &sc, const BatchView &v, cudaStream_t st, bool timed) {
+static int enqueue_tail_index(gcra_engine *h, Scratch &sc, const BatchView &v, bool compact, int64_t now_batch, cudaStream_t st,
+                              bool timed) {
     const u32 *n_res = reinterpret_cast<const u32 *>(sc.ctrl_block) + RC_NRES;
     const uint32_t n_max = std::min<uint32_t>(view_max_rows(v), h->max_batch);
     u64 *rs = nullptr;
+    // this set's bitmap has been read for the last time (pass C): cleared here, off stage 2's stream, for its next
+    // use (pass A' of the batch that takes this set again, and the PEND bits the batch before that one leaves)
+    CK(cudaMemsetAsync(sc.bitmap, 0, h->bm_words * sizeof(u32), st));
+    CK(cudaMemsetAsync(sc.pend, 0, h->pend_words * sizeof(u32), st));   // (the bits the previous batch left: read by pass B)
     if (timed) CK(cudaEventRecord(h->evd[5], st));
     RC(enqueue_sort(h, sc, n_max, n_res, st, &rs));
     if (timed) CK(cudaEventRecord(h->evd[6], st));
     OutMap om{};
     om.out = nullptr;
-    om.ridx = sc.ridx;
+    om.by_row = 1;
+    om.compact = compact ? 1 : 0;
     om.view = v;
+    om.pol = h->d_pol;
+    om.npol = h->npol;
+    om.now_batch = now_batch;
     RC(enqueue_decide_sorted(h, sc, n_max, n_res, rs, om, st));
     if (timed) { CK(cudaEventRecord(h->ev[3], st)); h->ev_valid = true; CK(cudaEventRecord(h->evd[7], st)); h->evd_valid = true; }
     CK(cudaGetLastError());
@@ -685,7 +706,7 @@ static int enqueue_tail_index(gcra_engine *h, Scratch &sc, const BatchView &v, c
 static int enqueue_back_sorted(gcra_engine *h, Scratch &sc, const BatchView &v, const u64 *sorted, cudaStream_t st, bool timed) {
     OutMap om{};
     om.out = v.res0;
-    om.ridx = nullptr;
+    om.by_row = 0;
     RC(enqueue_decide_sorted(h, sc, v.n, nullptr, sorted, om, st));
     if (timed) { CK(cudaEventRecord(h->ev[3], st)); h->ev_valid = true; }
     CK(cudaGetLastError());
@@ -731,9 +752,10 @@ static int launch_batch(gcra_engine *h, uint32_t n, const void *d_req, bool comp
             RC(enqueue_mid_index(h, sc, next, v, compact, now_batch, false, st, timed));
             CK(cudaEventRecord(sc.ev_mid, st));
             sc.mid_recorded = true;
-            RC(enqueue_tail_index(h, sc, v, st, timed));
+            RC(enqueue_tail_index(h, sc, v, compact, now_batch, st, timed));
         } else {
             RC(enqueue_back_sorted(h, sc, v, sorted, st, timed));
+            sc.mid_recorded = false;
         }
     }
     CK(cudaEventRecord(sc.ev_back, st));
@@ -760,25 +782,40 @@ static int launch_pipelined_view(gcra_engine *h, const BatchView &v, uint32_t n_
     if (ready) CK(cudaStreamWaitEvent(fs, ready, 0));
     if (sc.back_recorded) CK(cudaStreamWaitEvent(fs, sc.ev_back, 0));   // scratch set free again
     u64 *sorted = nullptr;
-    const bool ip = v.nseg > 1 || use_index_path(h, n_rows);
+    // residue feedback: the newest pass-C count that has reached the host
+    bool residue_large = false;
+    for (int back = 1; back < gcra_engine::N_SCR; back++) {
+        Scratch &os = h->scr[(k + gcra_engine::N_SCR - back) % gcra_engine::N_SCR];
+        if (!os.mid_recorded || cudaEventQuery(os.ev_mid) != cudaSuccess) continue;
+        if (!os.nres_counted) { h->residue_seen += *os.h_nres; h->residue_batches_seen++; os.nres_counted = true; }
+        h->last_nres = *os.h_nres;
+        h->last_nres_rows = os.nres_rows;
+        residue_large = (uint64_t)*os.h_nres * 8 > os.nres_rows;
+        break;
+    }
+    bool ip = v.nseg > 1 || use_index_path(h, n_rows);
+    if (ip && v.nseg == 1 && h->adaptive) {
+        // Which pipeline?  The index-order pipeline wins while most requests are decided in passes B and C; when
+        // more than a quarter of a batch went through the sorted tail (keys spending a burst: every request
+        // changes the state), sorting everything once is cheaper: the next 31 batches take the sort pipeline,
+        // then the index-order pipeline is tried again.
+        if (h->sort_hold > 0) { h->sort_hold--; ip = false; }
+        else if (h->last_nres_rows && (uint64_t)h->last_nres * 4 > h->last_nres_rows) {
+            h->sort_hold = 31; h->last_nres = 0; h->last_nres_rows = 0; ip = false; h->n_path_switches++;
+        }
+    }
     RC(enqueue_front(h, sc, v, ip, compact, now_batch, fs, false, &sorted));
     CK(cudaEventRecord(sc.ev_front, fs));
     cudaStream_t ms = h->back_stream;
     CK(cudaStreamWaitEvent(ms, sc.ev_front, 0));
     // May stage 2 of this batch overlap the tail of the batch submitted just before?  Only if that batch left its
-    // PEND bits in this set's bitmap.  Keys the tail owns stay deferred for as long as they keep appearing (their
-    // requests go from tail to tail), so the overlap is given up -- stage 2 waits for every tail and ignores the
-    // PEND bits -- whenever the residue reported by an earlier batch has grown beyond 1/8 of its rows, and every
-    // 64 batches.
+    // PEND bits in this set's pend bitmap.  Keys the tail owns stay deferred for as long as they keep appearing
+    // (their requests go from tail to tail), so the overlap is given up -- stage 2 waits for every tail and ignores
+    // the PEND bits -- whenever the residue reported by an earlier batch has grown beyond 1/8 of its rows, and
+    // every 64 batches.
     bool overlap = ip && h->pend_set == (int)k;
     if (ip) {
-        for (int back = 1; back < gcra_engine::N_SCR; back++) {
-            Scratch &os = h->scr[(k + gcra_engine::N_SCR - back) % gcra_engine::N_SCR];
-            if (!os.mid_recorded || cudaEventQuery(os.ev_mid) != cudaSuccess) continue;
-            if (!os.nres_counted) { h->residue_seen += *os.h_nres; h->residue_batches_seen++; os.nres_counted = true; }
-            if ((uint64_t)*os.h_nres * 8 > os.nres_rows && h->since_drain >= 2) overlap = false;
-            break;
-        }
+        if (residue_large && h->since_drain >= 2) overlap = false;
         if (h->since_drain >= 64) overlap = false;
         if (!overlap) { if (h->pend_set == (int)k) h->n_drains++; h->since_drain = 0; } else h->since_drain++;
     }
@@ -795,7 +832,7 @@ static int launch_pipelined_view(gcra_engine *h, const BatchView &v, uint32_t n_
         sc.mid_recorded = true;
         cudaStream_t ts = h->tail_stream;
         CK(cudaStreamWaitEvent(ts, sc.ev_mid, 0));
-        RC(enqueue_tail_index(h, sc, v, ts, false));
+        RC(enqueue_tail_index(h, sc, v, compact, now_batch, ts, false));
         CK(cudaEventRecord(sc.ev_back, ts));
         sc.back_recorded = true;
         h->pend_set = (int)kn;
@@ -803,6 +840,7 @@ static int launch_pipelined_view(gcra_engine *h, const BatchView &v, uint32_t n_
         return snapshot_async(h, n_rows, ts);
     }
     RC(enqueue_back_sorted(h, sc, v, sorted, ms, false));
+    sc.mid_recorded = false;   // (no residue count from this batch)
     CK(cudaEventRecord(sc.ev_back, ms));
     sc.back_recorded = true;
     h->pend_set = -1;
@@ -841,6 +879,7 @@ int32_t gcra_create(const gcra_config *cfg, gcra_engine **out) {
     cudaStreamCreateWithFlags(&h->in_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&h->aux2_stream, cudaStreamNonBlocking);
     // ONE front stream shared by all scratch sets (front halves run one after another; since ingest only CASes
     // the keys array they could overlap as well -- not measured yet)
     cudaStreamCreateWithFlags(&h->front_stream[0], cudaStreamNonBlocking);
@@ -862,16 +901,18 @@ int32_t gcra_create(const gcra_config *cfg, gcra_engine **out) {
     const size_t mb = h->max_batch;
     const uint32_t stiles = (uint32_t)((mb + SORT_TILE - 1) / SORT_TILE);
     {
-        // index-order pipeline: batch bitmap of 4-bit entries, 16 entries per row of the largest batch
-        // (a slot shares its entry with another slot of the batch with probability ~1/16), 64 K .. 64 M entries
-        uint32_t lg = ceil_log2(std::max<uint64_t>(16ULL * mb, 1ULL << 16));
-        if (lg > 26) lg = 26;
+        // index-order pipeline: hashed batch counters (16 bits) and pend bits, 8 entries per row of the largest
+        // batch (n distinct slots share their entry with probability ~1/8), 64 K .. 16 M entries
+        uint32_t lg = ceil_log2(std::max<uint64_t>(8ULL * mb, 1ULL << 16));
+        if (lg > 24) lg = 24;
         h->bm_mask = (1u << lg) - 1;
-        h->bm_words = (size_t)1 << (lg - 3);      // 4-bit entries, 8 per word
+        h->bm_words = (size_t)1 << (lg - 1);      // 16-bit counters, 2 per word
+        h->pend_words = (size_t)1 << (lg - 5);    // 1 bit per entry
         h->index_min = 32768;
-        if (const char *g = getenv("GCRA_INDEX_MIN")) h->index_min = (uint32_t)atoll(g);
-        if (cfg->flags & GCRA_FLAG_INDEX_PATH) h->index_min = SMALL_MAX + 1;
-        if (cfg->flags & GCRA_FLAG_SORT_PATH) h->index_min = 0;
+        if (const char *g = getenv("GCRA_INDEX_MIN")) { h->index_min = (uint32_t)atoll(g); h->adaptive = false; }
+        if (cfg->flags & GCRA_FLAG_INDEX_PATH) { h->index_min = SMALL_MAX + 1; h->adaptive = false; }
+        if (cfg->flags & GCRA_FLAG_SORT_PATH) { h->index_min = 0; h->adaptive = false; }
+        if (const char *g = getenv("GCRA_ADAPTIVE")) h->adaptive = atoi(g) != 0;
         h->prefetch_state = 0;
         if (const char *g = getenv("GCRA_PREFETCH")) h->prefetch_state = atoi(g);
         int sms = 148, nb = 0;
@@ -880,6 +921,9 @@ int32_t gcra_create(const gcra_config *cfg, gcra_engine **out) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, probe_kernel<true>, TILE_THREADS, 0) == cudaSuccess && nb > 0) h->grid_probe[1] = (uint32_t)(nb * sms);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decide_index_kernel<false>, TILE_THREADS, 0) == cudaSuccess && nb > 0) h->grid_decide[0] = (uint32_t)(nb * sms);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decide_index_kernel<true>, TILE_THREADS, 0) == cudaSuccess && nb > 0) h->grid_decide[1] = (uint32_t)(nb * sms);
+        // tuning: CTAs per SM of the persistent kernels (fewer leave room for the other stages' kernels)
+        if (const char *g = getenv("GCRA_CTAS_PROBE")) { uint32_t c = (uint32_t)atoi(g) * sms; if (c) { h->grid_probe[0] = std::min(h->grid_probe[0], c); h->grid_probe[1] = std::min(h->grid_probe[1], c); } }
+        if (const char *g = getenv("GCRA_CTAS_DECIDE")) { uint32_t c = (uint32_t)atoi(g) * sms; if (c) { h->grid_decide[0] = std::min(h->grid_decide[0], c); h->grid_decide[1] = std::min(h->grid_decide[1], c); } }
     }
     bool ok = cudaMalloc(&h->d_req, mb * sizeof(gcra_request)) == cudaSuccess &&
               cudaMalloc(&h->d_res, mb * sizeof(gcra_result)) == cudaSuccess &&
@@ -902,7 +946,8 @@ int32_t gcra_create(const gcra_config *cfg, gcra_engine **out) {
              cudaEventCreateWithFlags(&sc.ev_back, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&sc.ev_mid, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&sc.ev_fork, cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&sc.ev_join, cudaEventDisableTiming) == cudaSuccess;
+             cudaEventCreateWithFlags(&sc.ev_join, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&sc.ev_join2, cudaEventDisableTiming) == cudaSuccess;
         ok = ok && alloc_index_scratch(h, sc, h->max_batch) == GCRA_OK;
     }
     if (!ok) return fail("scratch allocation", cudaGetLastError());
@@ -956,9 +1001,9 @@ void gcra_destroy(gcra_engine *h) {
     for (auto &sc : h->scr) {
         cudaFree(sc.drec); cudaFree(sc.keys_a); cudaFree(sc.keys_b); cudaFree(sc.hist); cudaFree(sc.tot);
         cudaFree(sc.long_runs); cudaFree(sc.giant_runs); cudaFree(sc.long_count);
-        cudaFree(sc.slot_arr); cudaFree(sc.flags); cudaFree(sc.bitmap); cudaFree(sc.ctrl_block); cudaFree(sc.ridx);
+        cudaFree(sc.slot_arr); cudaFree(sc.flags); cudaFree(sc.bitmap); cudaFree(sc.pend); cudaFree(sc.ctrl_block);
         cudaFreeHost(sc.h_nres);
-        cudaEventDestroy(sc.ev_front); cudaEventDestroy(sc.ev_mid); cudaEventDestroy(sc.ev_back); cudaEventDestroy(sc.ev_fork); cudaEventDestroy(sc.ev_join);
+        cudaEventDestroy(sc.ev_front); cudaEventDestroy(sc.ev_mid); cudaEventDestroy(sc.ev_back); cudaEventDestroy(sc.ev_fork); cudaEventDestroy(sc.ev_join); cudaEventDestroy(sc.ev_join2);
     }
     cudaFree(h->d_req); cudaFree(h->d_res); cudaFree(h->route_counts); cudaFree(h->d_pol); cudaFree(h->d_op);
     cudaFreeHost(h->h_op); cudaFreeHost(h->h_counters); cudaFreeHost(h->h_snap);
@@ -967,7 +1012,7 @@ void gcra_destroy(gcra_engine *h) {
     for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 8; i++) cudaEventDestroy(h->evd[i]);
     cudaEventDestroy(h->ev_sweep[0]); cudaEventDestroy(h->ev_sweep[1]);
-    cudaStreamDestroy(h->stream); cudaStreamDestroy(h->in_stream); cudaStreamDestroy(h->out_stream); cudaStreamDestroy(h->aux_stream);
+    cudaStreamDestroy(h->stream); cudaStreamDestroy(h->in_stream); cudaStreamDestroy(h->out_stream); cudaStreamDestroy(h->aux_stream); cudaStreamDestroy(h->aux2_stream);
     cudaStreamDestroy(h->front_stream[0]);
     cudaStreamDestroy(h->back_stream); cudaStreamDestroy(h->tail_stream); cudaEventDestroy(h->ev_ready);
     delete h;
@@ -1259,6 +1304,7 @@ int32_t gcra_get_stats(gcra_engine *h, gcra_stats *out) {
     out->residue_rows = h->residue_seen;
     out->residue_batches = h->residue_batches_seen;
     out->drains = h->n_drains;
+    out->path_switches = h->n_path_switches;
     return GCRA_OK;
 }
 
@@ -1277,6 +1323,7 @@ int32_t gcra_sync(gcra_engine *h) {
     CK(cudaStreamSynchronize(h->back_stream));
     CK(cudaStreamSynchronize(h->tail_stream));
     CK(cudaStreamSynchronize(h->aux_stream));
+    CK(cudaStreamSynchronize(h->aux2_stream));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaStreamSynchronize(h->out_stream));
     return GCRA_OK;

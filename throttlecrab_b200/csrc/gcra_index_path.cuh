@@ -13,8 +13,7 @@
 // sector and the 16-byte state pair), then the sort path on the residue only:
 //
 //   A  probe_kernel          TMA-staged request tile, validation, key -> slot probe/claim (gcra_device.cuh);
-//                            writes slot[i]
-//   A' note_kernel           marks every slot in a hashed batch bitmap (seen / seen twice)
+//                            writes slot[i]; counts every slot in hashed batch counters (>= 2: the key is shared)
 //   B  decide_index_kernel   decide(S0, request) for every request, result written in place.  A request whose
 //                            slot was seen once is alone on its key: its new state is committed right away.
 //                            A state-changing request on a shared slot records its index with
@@ -27,7 +26,7 @@
 //
 // The three stages (A+A' | B+C | residue) of consecutive batches run on three streams.  So that B+C of batch
 // j+1 may overlap the residue of batch j, pass C leaves a PEND bit for every key it sends to the residue in the
-// NEXT batch's bitmap: batch j+1 does not evaluate requests on such keys in pass B, it defers them to its own
+// NEXT batch's pend bitmap: batch j+1 does not evaluate requests on such keys in pass B, it defers them to its own
 // residue (residues run strictly one after another).
 //
 // In the steady state of a rate limiter the hot keys are saturated (0-1 state changes per tick), so the
@@ -83,18 +82,23 @@ __device__ __forceinline__ void stage_tile(unsigned char *stage, u64 *bar, const
     parity ^= 1;
 }
 
-// The batch bitmap: four bits per entry (entry = slot & mask), eight entries per 32-bit word.
-//   SEEN    some request of THIS batch resolved to a slot of the entry
-//   SHARED  at least two did (then every one of them takes the mark / resolve route)
-//   PEND    written by the PREVIOUS batch's pass C: a slot of the entry still has residue requests in that batch's
-//           sorted tail, which may run concurrently with this batch's passes B and C; this batch's requests on
-//           such a slot are deferred to its own tail (tails run one after another)
-// A hashed index only merges slots: a false SHARED / PEND verdict costs time, never exactness.
-constexpr u32 BM_SEEN = 1, BM_SHARED = 2, BM_PEND = 4;
-
-__device__ __forceinline__ u32 bitmap_bits(const u32 *__restrict__ bm, u32 mask, u32 slot) {
+// Batch-local knowledge about slots, both hashed by (slot & mask) -- a hashed index only merges slots, and a false
+// "shared" / "pending" verdict costs time, never exactness:
+//   counters  16 bits per entry: how often the entry's slots occur in THIS batch, as far as that matters: pass A
+//             finds the distinct slots of every 256-row tile with a hash set in shared memory and adds
+//             min(count in the tile, 2) per distinct slot with ONE posted RED (no global atomic ever returns a
+//             value: returning atomics are throttled by the few that an SM can keep in flight).  >= 2 <=> shared.
+//             At most 2 x (number of tiles) per entry: the host keeps batches below 2^22 rows on this pipeline.
+//   pend      1 bit per entry, written by the PREVIOUS batch's pass C: a slot of the entry still has residue
+//             requests in that batch's sorted tail, which may run concurrently with this batch's passes B and C;
+//             this batch's requests on such a slot are deferred to its own tail (tails run one after another)
+__device__ __forceinline__ u32 counter_of(const u32 *__restrict__ cnt, u32 mask, u32 slot) {
     const u32 e = slot & mask;
-    return (__ldg(bm + (e >> 3)) >> ((e & 7) * 4)) & 0xF;
+    return (__ldg(cnt + (e >> 1)) >> ((e & 1) * 16)) & 0xFFFF;
+}
+__device__ __forceinline__ bool pend_of(const u32 *__restrict__ pend, u32 mask, u32 slot) {
+    const u32 e = slot & mask;
+    return (__ldg(pend + (e >> 5)) >> (e & 31)) & 1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -103,6 +107,8 @@ __device__ __forceinline__ u32 bitmap_bits(const u32 *__restrict__ bm, u32 mask,
 // Persistent CTAs over the tiles, software-pipelined one tile deep: while tile t is probed, the request tile t+1
 // already sits in the second stage buffer (bulk async copy) and its rows' first-choice key sectors are in
 // flight into registers -- a row's DRAM round trip overlaps the work of a whole tile instead of stalling it.
+constexpr u32 NOTE_HASH_BITS = 9, NOTE_HASH = 1u << NOTE_HASH_BITS;   // hash set of one 256-row tile (load <= 1/2)
+
 struct KeyProbe {
     u64 k;            // stored key
     u32 b1, b2;       // bucket choices
@@ -138,10 +144,14 @@ __device__ __forceinline__ void issue_tile(unsigned char *stage, u64 *bar, const
 template <bool COMPACT>
 __global__ void __launch_bounds__(TILE_THREADS)
 probe_kernel(Table t, BatchView b, const PolicyDerived *__restrict__ pol, u32 npol, i64 now_batch,
-             u32 *__restrict__ slot_arr, int prefetch_state) {
+             u32 *__restrict__ slot_arr, u32 *__restrict__ counters, u32 bm_mask, int prefetch_state) {
     constexpr u32 RSZ = COMPACT ? sizeof(gcra_request16) : sizeof(gcra_request);
     __shared__ __align__(128) unsigned char stage[2][TILE_THREADS * RSZ];
     __shared__ __align__(8) u64 bar[2];
+    // the distinct slots of the current tile and how often each occurs (see "counters" above)
+    __shared__ u32 hkey[NOTE_HASH];
+    __shared__ u32 hcnt[NOTE_HASH];
+    for (u32 i = threadIdx.x; i < NOTE_HASH; i += TILE_THREADS) { hkey[i] = 0xFFFFFFFFu; hcnt[i] = 0; }
     if (threadIdx.x == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
@@ -186,10 +196,28 @@ probe_kernel(Table t, BatchView b, const PolicyDerived *__restrict__ pol, u32 np
             }
             slot_arr[row] = slot;
             if (status != 0) { write_result(b.res_at(row), 0, 0, 0, status, 0); n_err++; }
-            // the state pair is what pass B touches next: optionally pull its sector into L2 now
-            else if (prefetch_state) asm volatile("prefetch.global.L2 [%0];" ::"l"(&t.state[slot]));
+            else {
+                // the state pair is what pass B touches next: optionally pull its sector into L2 now
+                if (prefetch_state) asm volatile("prefetch.global.L2 [%0];" ::"l"(&t.state[slot]));
+                u32 h = (slot * 0x9E3779B1u) >> (32 - NOTE_HASH_BITS);
+                for (;;) {
+                    const u32 old = atomicCAS(&hkey[h], 0xFFFFFFFFu, slot);
+                    if (old == 0xFFFFFFFFu || old == slot) { atomicAdd(&hcnt[h], 1u); break; }
+                    h = (h + 1) & (NOTE_HASH - 1);
+                }
+            }
         }
-        __syncthreads();   // everybody is done with stage[buf]
+        __syncthreads();   // everybody is done with stage[buf]; the tile's hash set is complete
+        // one posted add per distinct slot of the tile (result unused: RED.ADD), and the set is empty again
+        for (u32 i = threadIdx.x; i < NOTE_HASH; i += TILE_THREADS) {
+            const u32 sl = hkey[i];
+            if (sl == 0xFFFFFFFFu) continue;
+            const u32 e = sl & bm_mask;
+            atomicAdd(counters + (e >> 1), min(hcnt[i], 2u) << ((e & 1) * 16));
+            hkey[i] = 0xFFFFFFFFu;
+            hcnt[i] = 0;
+        }
+        __syncthreads();
         if (!has_nxt) break;
         tile += G;
         cur = nxt;
@@ -206,46 +234,36 @@ probe_kernel(Table t, BatchView b, const PolicyDerived *__restrict__ pol, u32 np
     }
 }
 
-// pass A': note every slot of the batch in the bitmap.  Lanes of a warp that hold the same slot elect one of
-// them, which issues ONE atomic: a no-return OR of SEEN|SHARED when the warp alone
-// already shows the slot twice, else a returning OR of SEEN (a second arrival then ORs SHARED in).
-__global__ void __launch_bounds__(TILE_THREADS)
-note_kernel(BatchView b, u32 null_slot, const u32 *__restrict__ slot_arr, u32 *__restrict__ bitmap, u32 bm_mask) {
-    const u32 lane = threadIdx.x & 31;
-    const u32 lt = (1u << lane) - 1;
-    for (u32 tile = blockIdx.x;; tile += gridDim.x) {
-        TileRef tr;
-        if (!tile_lookup(b, tile, 0, tr)) break;
-        const bool in_range = threadIdx.x < tr.cnt;
-        const u32 slot = in_range ? slot_arr[tr.row0 + threadIdx.x] : null_slot;
-        const bool valid = slot != null_slot;
-        const u32 peers = __match_any_sync(0xffffffffu, valid ? slot : (0x80000000u | lane));   // slot ids < 2^31
-        if (valid && (peers & lt) == 0) {
-            const u32 e = slot & bm_mask, sh = (e & 7) * 4;
-            u32 *w = bitmap + (e >> 3);
-            // hot keys: after their first arrivals everybody finds the entry complete and leaves it alone.  The look
-            // goes through L1 (bits are only ever set while this kernel runs: a stale line shows a subset, which
-            // at worst costs the atomic), so a hot entry is read from L2 once per SM, not once per warp -- an LTS
-            // slice serves requests to one sector, and atomics on one address, one after another.
-            const u32 cur = (*w >> sh) & 0xF;
-            if ((cur & (BM_SEEN | BM_SHARED)) != (BM_SEEN | BM_SHARED)) {
-                if (__popc(peers) >= 2) {
-                    atomicOr(w, (BM_SEEN | BM_SHARED) << sh);          // result unused: RED
-                } else if (cur & BM_SEEN) {
-                    atomicOr(w, BM_SHARED << sh);
-                } else {
-                    const u32 old = atomicOr(w, BM_SEEN << sh);
-                    if ((old >> sh) & BM_SEEN) { if (!((old >> sh) & BM_SHARED)) atomicOr(w, BM_SHARED << sh); }
-                }
-            }
-        }
+constexpr int RES_ROWS = 4;                                  // rows per thread (note, resolve)
+constexpr int RES_TILE = TILE_THREADS * RES_ROWS;            // rows per CTA tile: a whole number of probe tiles
+
+// tile `t` of RES_TILE rows in row-id order (segments are padded to whole tiles in the row-id space)
+__device__ __forceinline__ bool res_tile_lookup(const BatchView &b, u32 t, u32 &row0, u32 &cnt) {
+    if (b.nseg == 1) {
+        const u64 r0 = (u64)t * RES_TILE;
+        if (r0 >= b.n) return false;
+        row0 = (u32)r0;
+        cnt = min((u32)RES_TILE, b.n - row0);
+        return true;
     }
+    const u32 cap = 1u << b.cap_shift;
+    for (u32 s = 0; s < b.nseg; s++) {
+        const u32 c = min(__ldg(&b.dev_counts[s]), cap);
+        const u32 tiles = (c + RES_TILE - 1) / RES_TILE;
+        if (t < tiles) {
+            row0 = (s << b.cap_shift) | (t * RES_TILE);
+            cnt = min((u32)RES_TILE, c - t * RES_TILE);
+            return true;
+        }
+        t -= tiles;
+    }
+    return false;
 }
 
 // ---------------------------------------------------------------------------------------------
 // pass B: decide every request against the state its key had when the batch started
 // ---------------------------------------------------------------------------------------------
-constexpr unsigned char F_ALLOWED = 1, F_MUTATES = 2, F_EXP_HIT = 4, F_DEFER = 8;
+constexpr unsigned char F_ALLOWED = 1, F_MUTATES = 2, F_EXP_HIT = 4, F_DEFER = 8, F_SHARED = 16;
 
 __device__ __forceinline__ u64 mark_value(u32 epoch, u32 row) { return ((u64)(~epoch) << 32) | row; }
 
@@ -253,12 +271,12 @@ __device__ __forceinline__ u64 mark_value(u32 epoch, u32 row) { return ((u64)(~e
 #define GCRA_B_MINBLOCKS 1
 #endif
 // Persistent CTAs, software-pipelined: while tile t is decided, tile t+1's requests sit in the second stage buffer,
-// its rows' state pairs and bitmap words are in flight into registers, and tile t+2's slots are being read.
+// its rows' state pairs, counters and pend bits are in flight into registers, and tile t+2's slots are being read.
 template <bool COMPACT>
 __global__ void __launch_bounds__(TILE_THREADS, GCRA_B_MINBLOCKS)
 decide_index_kernel(Table t, BatchView b, const PolicyDerived *__restrict__ pol, u32 npol, i64 now_batch,
-                    const u32 *__restrict__ slot_arr, const u32 *__restrict__ bitmap, u32 bm_mask,
-                    unsigned char *__restrict__ flags, u32 epoch, u32 pend_mask, u32 dbg) {
+                    const u32 *__restrict__ slot_arr, const u32 *__restrict__ counters, const u32 *__restrict__ pend,
+                    u32 bm_mask, unsigned char *__restrict__ flags, u32 epoch, u32 honour_pend, u32 dbg) {
     constexpr u32 RSZ = COMPACT ? sizeof(gcra_request16) : sizeof(gcra_request);
     __shared__ __align__(128) unsigned char stage[2][TILE_THREADS * RSZ];
     __shared__ __align__(8) u64 bar[2];
@@ -283,9 +301,11 @@ decide_index_kernel(Table t, BatchView b, const PolicyDerived *__restrict__ pol,
     u32 slot_n = (has_nxt && threadIdx.x < nxt.cnt) ? slot_arr[nxt.row0 + threadIdx.x] : t.null_slot;
     RunState s_c = {0, EXP_EMPTY, 0};
     u32 bits_c = 0;
+    // bits: F_SHARED (the batch holds the key at least twice) | F_DEFER (the previous batch's tail owns it)
     if (slot_c != t.null_slot) {
         if (!(dbg & 16)) load_state(t, slot_c, s_c);
-        if (!(dbg & 32)) bits_c = bitmap_bits(bitmap, bm_mask, slot_c) & pend_mask;
+        if (!(dbg & 32)) bits_c = (counter_of(counters, bm_mask, slot_c) >= 2 ? F_SHARED : 0) |
+                                  ((honour_pend && pend_of(pend, bm_mask, slot_c)) ? F_DEFER : 0);
     }
     u32 n_allowed = 0, n_denied = 0, exp_hits = 0, real_inc = 0;
     for (;;) {
@@ -294,7 +314,8 @@ decide_index_kernel(Table t, BatchView b, const PolicyDerived *__restrict__ pol,
         u32 bits_n = 0;
         if (slot_n != t.null_slot) {
             if (!(dbg & 16)) load_state(t, slot_n, s_n);
-            if (!(dbg & 32)) bits_n = bitmap_bits(bitmap, bm_mask, slot_n) & pend_mask;
+            if (!(dbg & 32)) bits_n = (counter_of(counters, bm_mask, slot_n) >= 2 ? F_SHARED : 0) |
+                                      ((honour_pend && pend_of(pend, bm_mask, slot_n)) ? F_DEFER : 0);
         }
         // the tile after that: its slots
         const bool has_nn = has_nxt && tile_lookup(b, tile + 2 * G, RSZ, nn);
@@ -306,9 +327,9 @@ decide_index_kernel(Table t, BatchView b, const PolicyDerived *__restrict__ pol,
         const u32 slot = slot_c;
         const RunState s = s_c;
         const u32 bits = bits_c;
-        if (slot != t.null_slot && (bits & BM_PEND)) {
-            // the previous batch still works on this key (or on one sharing its bitmap entry): not evaluated
-            // here, the whole key goes to this batch's sorted tail
+        if (slot != t.null_slot && (bits & F_DEFER)) {
+            // the previous batch still works on this key (or on one sharing its entry): not evaluated here, the
+            // whole key goes to this batch's sorted tail
             flags[row] = F_DEFER;
         } else if (slot != t.null_slot) {
             u64 key_hash;
@@ -322,8 +343,9 @@ decide_index_kernel(Table t, BatchView b, const PolicyDerived *__restrict__ pol,
             const bool mut = d.allowed && ((d.new_tat != s.tat) | (d.new_exp != s.exp));
             // a write over an entry that exists but is expired (adaptive_cleanup.rs:233,267)
             const bool hit = d.allowed && !d.live && s.exp >= 0;
-            if (!(bits & BM_SHARED)) {
+            if (!(bits & F_SHARED)) {
                 // the only request of the batch on this key: final, and its write is the key's only write
+                flags[row] = 0;
                 if (mut && !(dbg & 1)) {
                     const bool created = s.exp < 0;
                     RunState ns = {d.new_tat, d.new_exp, r.ei};
@@ -334,7 +356,7 @@ decide_index_kernel(Table t, BatchView b, const PolicyDerived *__restrict__ pol,
                 n_denied += d.allowed ? 0 : 1;
                 exp_hits += hit ? 1 : 0;
             } else {
-                flags[row] = (unsigned char)((d.allowed ? F_ALLOWED : 0) | (mut ? F_MUTATES : 0) | (hit ? F_EXP_HIT : 0));
+                flags[row] = (unsigned char)(F_SHARED | (d.allowed ? F_ALLOWED : 0) | (mut ? F_MUTATES : 0) | (hit ? F_EXP_HIT : 0));
                 if (mut && !(dbg & 4)) {
                     // marks only ever decrease while this kernel runs, so a (possibly stale, L1) value at or below
                     // mine proves an earlier state change is already recorded: hot keys cost one L2 read per SM
@@ -401,39 +423,13 @@ __device__ __forceinline__ u32 lookback(volatile u64 *__restrict__ status, u32 t
     return base;
 }
 
-constexpr int RES_ROWS = 4;                                  // rows per thread
-constexpr int RES_TILE = TILE_THREADS * RES_ROWS;            // rows per CTA tile: a whole number of probe tiles
-
-// tile `t` of RES_TILE rows in row-id order (segments are padded to whole tiles in the row-id space)
-__device__ __forceinline__ bool res_tile_lookup(const BatchView &b, u32 t, u32 &row0, u32 &cnt) {
-    if (b.nseg == 1) {
-        const u64 r0 = (u64)t * RES_TILE;
-        if (r0 >= b.n) return false;
-        row0 = (u32)r0;
-        cnt = min((u32)RES_TILE, b.n - row0);
-        return true;
-    }
-    const u32 cap = 1u << b.cap_shift;
-    for (u32 s = 0; s < b.nseg; s++) {
-        const u32 c = min(__ldg(&b.dev_counts[s]), cap);
-        const u32 tiles = (c + RES_TILE - 1) / RES_TILE;
-        if (t < tiles) {
-            row0 = (s << b.cap_shift) | (t * RES_TILE);
-            cnt = min((u32)RES_TILE, c - t * RES_TILE);
-            return true;
-        }
-        t -= tiles;
-    }
-    return false;
-}
-
 template <bool COMPACT>
 __global__ void __launch_bounds__(TILE_THREADS)
 resolve_kernel(Table t, BatchView b, const PolicyDerived *__restrict__ pol, u32 npol, i64 now_batch,
-               const u32 *__restrict__ slot_arr, const u32 *__restrict__ bitmap, u32 bm_mask,
+               const u32 *__restrict__ slot_arr, u32 bm_mask,
                const unsigned char *__restrict__ flags, u32 epoch, u32 *__restrict__ ctrl,
-               volatile u64 *__restrict__ tile_status, u64 *__restrict__ res_keys, u32 *__restrict__ ridx,
-               Req *__restrict__ drec, u32 *__restrict__ next_bitmap, u32 pend_mask, volatile u32 *__restrict__ host_nres) {
+               volatile u64 *__restrict__ tile_status, u64 *__restrict__ res_keys,
+               u32 *__restrict__ next_pend, volatile u32 *__restrict__ host_nres) {
     constexpr u32 RSZ = COMPACT ? sizeof(gcra_request16) : sizeof(gcra_request);
     __shared__ u32 part[TILE_THREADS / 32];
     __shared__ u32 sm_tile, sm_base;
@@ -454,13 +450,20 @@ resolve_kernel(Table t, BatchView b, const PolicyDerived *__restrict__ pol, u32 
             slot[k] = (threadIdx.x * RES_ROWS + k < cnt) ? slot_arr[first_row + k] : t.null_slot;
             residue[k] = false;
         }
+        // what pass B found out about each row: F_SHARED / F_DEFER (+ its verdict)
         u32 bits[RES_ROWS];
+        if (threadIdx.x * RES_ROWS + RES_ROWS <= cnt) {
+            const u32 f4 = *reinterpret_cast<const u32 *>(flags + first_row);
 #pragma unroll
-        for (int k = 0; k < RES_ROWS; k++) bits[k] = slot[k] != t.null_slot ? (bitmap_bits(bitmap, bm_mask, slot[k]) & pend_mask) : 0;
+            for (int k = 0; k < RES_ROWS; k++) bits[k] = slot[k] != t.null_slot ? ((f4 >> (8 * k)) & 0xFF) : 0;
+        } else {
+#pragma unroll
+            for (int k = 0; k < RES_ROWS; k++) bits[k] = slot[k] != t.null_slot ? flags[first_row + k] : 0;
+        }
         u64 mk[RES_ROWS];
 #pragma unroll
         for (int k = 0; k < RES_ROWS; k++) {
-            const bool look = (bits[k] & BM_SHARED) && !(bits[k] & BM_PEND);
+            const bool look = (bits[k] & F_SHARED) && !(bits[k] & F_DEFER);
             mk[k] = look ? t.mark[slot[k]] : ~0ULL;
         }
         u32 mine = 0;
@@ -468,15 +471,15 @@ resolve_kernel(Table t, BatchView b, const PolicyDerived *__restrict__ pol, u32 
         for (int k = 0; k < RES_ROWS; k++) {
             if (slot[k] == t.null_slot) continue;
             const u32 row = first_row + k;
-            if (bits[k] & BM_PEND) {
+            if (bits[k] & F_DEFER) {
                 residue[k] = true;                                   // deferred by pass B
-            } else if (bits[k] & BM_SHARED) {
+            } else if (bits[k] & F_SHARED) {
                 const bool has = (u32)(mk[k] >> 32) == ~epoch;
                 const u32 first = (u32)mk[k];
                 if (has && row > first) {
                     residue[k] = true;
                 } else {
-                    const unsigned char f = flags[row];
+                    const u32 f = bits[k];
                     n_allowed += (f & F_ALLOWED) ? 1 : 0;
                     n_denied += (f & F_ALLOWED) ? 0 : 1;
                     exp_hits += (f & F_EXP_HIT) ? 1 : 0;
@@ -518,16 +521,10 @@ resolve_kernel(Table t, BatchView b, const PolicyDerived *__restrict__ pol, u32 
             if (!residue[k]) continue;
             const u32 row = first_row + k;
             const u32 p = base + rank++;
-            u64 key_hash;
-            Req r;
-            parse_request<COMPACT>(b.req_at(row, RSZ), pol, npol, now_batch, key_hash, r);
-            res_keys[p] = ((u64)slot[k] << 32) | p;
-            ridx[p] = row;
-            reinterpret_cast<longlong2 *>(drec + p)[0] = make_longlong2(r.now, r.ei);
-            reinterpret_cast<longlong2 *>(drec + p)[1] = make_longlong2(r.dvt, r.q);
+            res_keys[p] = ((u64)slot[k] << 32) | row;     // the tail parses the request of row `row` itself
             // the next batch must keep off this key until this batch's tail is through with it
-            const u32 e = slot[k] & bm_mask, sh = (e & 7) * 4;
-            if (!((next_bitmap[e >> 3] >> sh) & BM_PEND)) atomicOr(next_bitmap + (e >> 3), BM_PEND << sh);   // (stale L1: subset)
+            const u32 e = slot[k] & bm_mask;
+            if (!((next_pend[e >> 5] >> (e & 31)) & 1)) atomicOr(next_pend + (e >> 5), 1u << (e & 31));   // (a stale L1 line shows a subset; result unused: RED)
         }
         __syncthreads();   // sm_tile / sm_base / part are reused by the next tile
     }

@@ -394,13 +394,18 @@ struct BatchView {
     }
 };
 
-// where the result of sorted position `p` goes: the sort path numbers requests by batch index (out + p);
-// the residue of the index-order pipeline numbers them by residue position and keeps their row ids aside
+// What the payload `i` of a sorted key stands for.  Sort pipeline: the batch index -- the derived request is
+// drec[i], the result goes to out + i.  Residue of the index-order pipeline: the row id -- the request is parsed
+// from the batch itself (req_at(i)), the result goes to the row's own place (res_at(i)).
 struct OutMap {
     gcra_result *out;
-    const u32 *ridx;             // residue position -> row id (nullptr: identity)
+    int by_row;                  // 0: sort pipeline, 1: residue of the index-order pipeline
+    int compact;                 // by_row: the batch holds gcra_request16 rows
     BatchView view;
-    __device__ __forceinline__ gcra_result *at(u32 p) const { return ridx ? view.res_at(ridx[p]) : out + p; }
+    const PolicyDerived *pol;
+    u32 npol;
+    i64 now_batch;
+    __device__ __forceinline__ gcra_result *at(u32 i) const { return by_row ? view.res_at(i) : out + i; }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -473,7 +478,14 @@ constexpr int LONG_THREADS = 512;
 constexpr int CLUSTER_CTAS = GCRA_CLUSTER;
 struct LongRun { u32 start, len; };
 
-__device__ __forceinline__ void load_req(const Req *__restrict__ drec, u32 idx, Req &r) {
+__device__ __forceinline__ void load_req(const Req *__restrict__ drec, const OutMap &om, u32 idx, Req &r) {
+    if (om.by_row) {
+        // (rows in the residue passed validation in pass A: the status is 0)
+        u64 key_hash;
+        if (om.compact) parse_request<true>(om.view.req_at(idx, sizeof(gcra_request16)), om.pol, om.npol, om.now_batch, key_hash, r);
+        else parse_request<false>(om.view.req_at(idx, sizeof(gcra_request)), nullptr, 0, 0, key_hash, r);
+        return;
+    }
     longlong2 a = reinterpret_cast<const longlong2 *>(drec + idx)[0];
     longlong2 b = reinterpret_cast<const longlong2 *>(drec + idx)[1];
     r.now = a.x; r.ei = a.y; r.dvt = b.x; r.q = b.y;
@@ -518,7 +530,9 @@ constexpr int DECIDE_THREADS = GCRA_DECIDE_THREADS;   // warps are independent: 
 __device__ __forceinline__ void decide_chunk(const Table &t, const u64 *sorted, const Req *__restrict__ drec, u32 n,
                                              const OutMap &out, LongRun *__restrict__ long_runs,
                                              LongRun *__restrict__ giant_runs, u32 *__restrict__ long_count,
-                                             u32 warp_global, u32 lane) {
+                                             u32 warp_global, u32 lane, int mode = 0) {
+    // mode 0: find the hot runs (work lists) and decide everything else; 1: only find the hot runs; 2: only
+    // decide (the lists were written by a mode-1 launch, the hot-run kernels already work on them)
     const u32 base = warp_global * 32;
     if (base >= n) return;   // whole warp
 
@@ -561,7 +575,7 @@ __device__ __forceinline__ void decide_chunk(const Table &t, const u64 *sorted, 
         const u32 end = run_end(sorted, n, base + 32, slot31, lane);
         if (end - run_start >= LONG_RUN_MIN) {
             // hot key: hand the whole run (including its lanes here) to decide_long_kernel
-            if (lane == 0) {
+            if (lane == 0 && mode != 2) {
                 const bool giant = end - run_start >= GIANT_RUN_MIN;
                 u32 w = atomicAdd(long_count + (giant ? 1 : 0), 1u);
                 LongRun *dst = giant ? giant_runs : long_runs;
@@ -572,10 +586,11 @@ __device__ __forceinline__ void decide_chunk(const Table &t, const u64 *sorted, 
             cont = false;
         }
     }
+    if (mode == 1) return;
 
     Req r = {0, 0, 0, 0};
     const u32 idx = (u32)e;
-    if (mine) load_req(drec, idx, r);
+    if (mine) load_req(drec, out, idx, r);
     // run heads read the entry; the run's lanes get it by shuffle
     RunState s = {0, EXP_EMPTY, 0};
     if (head && mine) load_state(t, slot, s);
@@ -623,7 +638,7 @@ __device__ __forceinline__ void decide_chunk(const Table &t, const u64 *sorted, 
         u64 e2 = b2 + lane < n ? sorted[b2 + lane] : ~0ULL;
         bool in_run = (u32)(e2 >> 32) == slot31 && b2 + lane < n;
         Req r2 = {0, 0, 0, 0};
-        if (in_run) load_req(drec, (u32)e2, r2);
+        if (in_run) load_req(drec, out, (u32)e2, r2);
         for (;;) {
             const u32 rm = __ballot_sync(0xffffffffu, in_run);   // a prefix (sorted)
             if (rm == 0) break;
@@ -635,7 +650,7 @@ __device__ __forceinline__ void decide_chunk(const Table &t, const u64 *sorted, 
             if (rm == 0xffffffffu) {
                 e3 = b3 + lane < n ? sorted[b3 + lane] : ~0ULL;
                 in3 = (u32)(e3 >> 32) == slot31 && b3 + lane < n;
-                if (in3) load_req(drec, (u32)e3, r3);
+                if (in3) load_req(drec, out, (u32)e3, r3);
             }
             RunState s2 = cs;
             Decision f2;
@@ -677,11 +692,11 @@ __device__ __forceinline__ void decide_chunk(const Table &t, const u64 *sorted, 
 __global__ void __launch_bounds__(DECIDE_THREADS, 1024 / DECIDE_THREADS)
 decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ drec, u32 n_host,
               const u32 *__restrict__ n_dev, OutMap out, LongRun *__restrict__ long_runs,
-              LongRun *__restrict__ giant_runs, u32 *__restrict__ long_count) {
+              LongRun *__restrict__ giant_runs, u32 *__restrict__ long_count, int mode) {
     const u32 n = sort_count(n_host, n_dev);
     const u32 warps_total = gridDim.x * (DECIDE_THREADS / 32);
     for (u32 wg = (blockIdx.x * DECIDE_THREADS + threadIdx.x) >> 5; wg * 32 < n; wg += warps_total)
-        decide_chunk(t, sorted, drec, n, out, long_runs, giant_runs, long_count, wg, threadIdx.x & 31);
+        decide_chunk(t, sorted, drec, n, out, long_runs, giant_runs, long_count, wg, threadIdx.x & 31, mode);
 }
 
 // Small batches (n < LONG_RUN_MIN, e.g. one RateLimiter::rate_limit call or a lightly loaded actor): ONE CTA
@@ -717,7 +732,7 @@ small_batch_kernel(Table t, const void *__restrict__ req_base, const PolicyDeriv
     __threadfence_block();   // drec / state written above are read below by other warps of this CTA
     OutMap om;
     om.out = out;
-    om.ridx = nullptr;
+    om.by_row = 0;
     decide_chunk(t, keys, drec, n, om, nullptr, nullptr, nullptr, tid >> 5, tid & 31);
 }
 
@@ -814,13 +829,13 @@ decide_runs_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restric
         bool active = gpos < len;
         u32 idx = 0;
         Req r = {0, 0, 0, 0};
-        if (active) { idx = (u32)sorted[start + gpos]; load_req(drec, idx, r); }
+        if (active) { idx = (u32)sorted[start + gpos]; load_req(drec, out, idx, r); }
         for (u32 off = 0; off < len; off += STRIDE) {
             const u32 noff = off + STRIDE;
             const bool nactive = noff + gpos < len;
             u32 nidx = 0;
             Req nr = {0, 0, 0, 0};
-            if (nactive) { nidx = (u32)sorted[start + noff + gpos]; load_req(drec, nidx, nr); }
+            if (nactive) { nidx = (u32)sorted[start + noff + gpos]; load_req(drec, out, nidx, nr); }
             bool pending = active;
             for (;;) {
                 const bool fsm = n_changes >= FSM_AFTER;
@@ -951,7 +966,7 @@ decide_runs_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restric
             cd.get(cur, fs.tat, fs.exp);
             if (fs.tat != s0.tat || fs.exp != s0.exp) {
                 Req first;
-                load_req(drec, (u32)sorted[start], first);
+                load_req(drec, out, (u32)sorted[start], first);
                 fs.ei = first.ei;
                 store_state(t, slot, fs, was_phantom);
                 if (was_phantom) real_inc++;
