@@ -235,6 +235,44 @@ int32_t gcra_shard_join(gcra_engine *h, void *stream);
 /* make `stream` wait for the results of the tick submitted `ticks_back` submissions ago (0 = latest, < 3) */
 int32_t gcra_shard_wait_tick(gcra_engine *h, uint32_t ticks_back, void *stream);
 
+/* ---- the sharded tick over NVLink peer memory: no NCCL in the data path, no host synchronisation -------------
+ * Every rank owns a window of device memory (inboxes, outboxes, flags) that all peers map.  The partition kernel
+ * stores each request row straight into its owner's inbox, the owner's engine runs over the inbox as one batch of
+ * `world` segments and stores every result straight into the sender's outbox, one-warp kernels wait on tick
+ * numbers that peers publish with system-scope release stores (csrc/gcra_p2p.cuh).  Same ordering contract as
+ * gcra_shard_*: within a tick rank r's rows precede rank r+1's; ticks are decided in submission order; every rank
+ * submits every tick.  gcra_p2p_prepare allocates the window (cap_rows = most rows a rank submits per tick) and
+ * returns its CUDA IPC handle (64 bytes) and its address; the caller hands all ranks' handles (other processes) or
+ * addresses (engines of one process) to gcra_p2p_connect. */
+int32_t gcra_p2p_prepare(gcra_engine *h, int32_t rank, int32_t world, uint32_t cap_rows, void *ipc_handle_out_64,
+                         void **window_out);
+int32_t gcra_p2p_connect(gcra_engine *h, const void *ipc_handles_world_x_64, void *const *windows);
+int32_t gcra_p2p_submit(gcra_engine *h, uint64_t n, const gcra_request *d_req, gcra_result *d_res,
+                        void *ready_stream);
+/* the two halves of gcra_p2p_submit, for callers that drive several engines from ONE process: enqueue the route
+ * of every engine before the first finish (a finish enqueues kernels that wait for the other engines' routes) */
+int32_t gcra_p2p_submit_route(gcra_engine *h, uint64_t n, const gcra_request *d_req, void *ready_stream);
+int32_t gcra_p2p_submit_finish(gcra_engine *h, gcra_result *d_res);
+int32_t gcra_p2p_wait_tick(gcra_engine *h, uint32_t ticks_back, void *stream);
+int32_t gcra_p2p_join(gcra_engine *h, void *stream);
+/* *error = 1 when a wait on this rank gave up after ~20 s (a peer never delivered a tick) */
+int32_t gcra_p2p_error(gcra_engine *h, uint32_t *error);
+
+/* ---- the batch-draining actor: per-request callers in front of the batched engine ---------------------------
+ * replaces RateLimiterActor / RateLimiterHandle (throttlecrab-server/src/actor.rs:68-82,217-236): one actor thread
+ * owns the engine and applies requests strictly in arrival order; gcra_actor_throttle is thread-safe and blocks
+ * until its own result is there; everything that queues up while a batch is on the GPU becomes the next batch.
+ * buffer_size = the bounded channel (0 -> 100000, the server's --buffer-size), max_batch = most requests per
+ * drain (0 -> the engine's max_batch).  While an actor exists it is the ONLY caller of the engine. */
+typedef struct gcra_actor gcra_actor;
+int32_t gcra_actor_create(gcra_engine *h, uint32_t buffer_size, uint32_t max_batch, gcra_actor **out);
+int32_t gcra_actor_throttle(gcra_actor *a, const void *key, uint64_t len, int64_t max_burst,
+                            int64_t count_per_period, int64_t period, int64_t quantity, int64_t now_ns,
+                            gcra_result *out);
+/* out[0] batches run, out[1] requests served, out[2] largest batch */
+int32_t gcra_actor_stats(gcra_actor *a, uint64_t out[3]);
+void gcra_actor_destroy(gcra_actor *a);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,7 +14,10 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <atomic>
 #include <thread>
+#include <pthread.h>
+#include <sched.h>
 #include <vector>
 
 typedef unsigned __int128 u128;
@@ -358,10 +361,26 @@ extern "C" double ora_replay_sharded(ora_store **stores, int threads, uint64_t n
     /* pre-partition (untimed): shard t owns key_id % threads == t, index order kept */
     std::vector<std::vector<uint32_t>> idx(threads);
     for (uint64_t i = 0; i < n; i++) idx[req[i].key_id % (uint64_t)threads].push_back((uint32_t)i);
+    /* one pinned thread per store; all threads start together, the clock runs from the common start to the
+     * last join (thread creation is not timed) */
     std::vector<std::thread> th;
-    auto t0 = std::chrono::steady_clock::now();
+    std::atomic<int> ready{0};
+    std::atomic<bool> go{false};
+    cpu_set_t allowed;
+    CPU_ZERO(&allowed);
+    const bool have_mask = sched_getaffinity(0, sizeof(allowed), &allowed) == 0;
+    std::vector<int> cpus;
+    if (have_mask) for (int c = 0; c < CPU_SETSIZE; c++) if (CPU_ISSET(c, &allowed)) cpus.push_back(c);
     for (int t = 0; t < threads; t++) {
         th.emplace_back([&, t]() {
+            if (!cpus.empty()) {
+                cpu_set_t one;
+                CPU_ZERO(&one);
+                CPU_SET(cpus[t % cpus.size()], &one);
+                pthread_setaffinity_np(pthread_self(), sizeof(one), &one);
+            }
+            ready.fetch_add(1);
+            while (!go.load(std::memory_order_acquire)) { }
             char buf[32];
             ora_store *s = stores[t];
             for (uint32_t i : idx[t]) {
@@ -371,6 +390,9 @@ extern "C" double ora_replay_sharded(ora_store **stores, int threads, uint64_t n
             }
         });
     }
+    while (ready.load() < threads) std::this_thread::yield();
+    auto t0 = std::chrono::steady_clock::now();
+    go.store(true, std::memory_order_release);
     for (auto &x : th) x.join();
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }

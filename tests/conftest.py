@@ -48,4 +48,8 @@ def k1_path(request, monkeypatch):
 
 def pytest_generate_tests(metafunc):
     if metafunc.definition.get_closest_marker("gpu") and "k1_path" in metafunc.fixturenames:
+        for m in metafunc.definition.iter_markers("parametrize"):      # a test may pick its own pipelines
+            names = m.args[0] if isinstance(m.args[0], (list, tuple)) else [x.strip() for x in m.args[0].split(",")]
+            if "k1_path" in names:
+                return
         metafunc.parametrize("k1_path", list(K1_PATHS), indirect=True)

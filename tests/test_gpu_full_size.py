@@ -117,3 +117,104 @@ def test_full_size_sweep_round_trip(key_hash_of):
         lim.rate_limit_batch(ereq[a:a + TICK], out=again[a:a + TICK])
     assert first.tobytes() == again.tobytes()
     st.close()
+
+
+def test_full_size_full_trace_matches_oracle(key_hash_of):
+    """BASELINE configs[1], the WHOLE trace: 10 M-key warm pass + 3 Zipf ticks of 2^20 requests, every row against ONE
+    oracle store (the reference's semantics: one request at a time, rate_limiter.rs:102-250)."""
+    body = traces.config2(n_keys=N_KEYS, n_ticks=3, tick_size=TICK)
+    trace = np.concatenate([traces.warm_pass(N_KEYS), body])
+    res, st = _run(trace, key_hash_of, TICK)
+    st.close()
+    want = oracle.OracleStore(oracle.ADAPTIVE, capacity=N_KEYS, created_ns=traces.T0).replay(trace)
+    bad = first_mismatch(want, res, trace)
+    assert bad is None, bad
+
+
+@pytest.mark.parametrize("k1_path", ["auto", "sort"], indirect=True)
+def test_single_key_run_of_a_million_requests(k1_path):
+    """ONE key, 2^20 requests in ONE batch: varying policy, quantity and clock, so that the run holds thousands of
+    state changes and long saturated stretches (in the index-order pipeline: marks, residue, giant-run kernels;
+    in the sort pipeline: the cluster kernel's finite-state rounds)."""
+    n = TICK
+    rng = np.random.default_rng(5)
+    req = np.zeros(n, traces.REQ_DTYPE)
+    req["key"] = 7
+    # long stretches of one policy (saturation) with bursts of mixed ones
+    pol = np.repeat(rng.integers(0, 8, n // 4096 + 1), 4096)[:n]
+    mixed = rng.random(n) < 0.02
+    pol[mixed] = rng.integers(0, 8, int(mixed.sum()))
+    traces.fill_policy(req, pol)
+    req["quantity"] = rng.choice([0, 1, 1, 1, 1, 2, 5], n)
+    req["now_ns"] = traces.T0 + np.cumsum(rng.choice([0, 0, 0, 1000, 1_000_000, 50_000_000], n))
+    st = tc.ManualStore(capacity=1000, created_ns=traces.T0, max_batch=TICK)
+    lim = tc.RateLimiter(st)
+    ereq = np.empty(n, tc.REQ_DTYPE)
+    ereq["key_hash"] = tc.hash_key_ids(req["key"])
+    for f in ("max_burst", "count_per_period", "period", "quantity", "now_ns"):
+        ereq[f] = req[f]
+    res = lim.rate_limit_batch(ereq)
+    st.close()
+    want = oracle.OracleStore(oracle.PERIODIC, capacity=100, created_ns=traces.T0, p0=10**9).replay(req)
+    bad = first_mismatch(want, res, req)
+    assert bad is None, bad
+    assert 1000 < int(want["allowed"].sum()) < n - 1000
+
+
+@pytest.mark.parametrize("k1_path", ["auto"], indirect=True)
+def test_config3_100m_keys_sampled_parity_and_sweep(k1_path):
+    """BASELINE configs[2]: 100 M resident keys (table of 2^28 slots, 10 GB), uniform ticks of 2^20 requests.
+    Per-key independence: 20 000 sampled keys (their warm-pass row and every tick row) bit-exact against the oracle;
+    then the sweep at three clocks removes exactly the entries whose expiry has passed (adaptive_cleanup.rs:176-182)."""
+    n_keys, n_ticks = 100_000_000, 2
+    st = tc.ManualStore(capacity=n_keys, created_ns=traces.T0, max_batch=TICK)
+    lim = tc.RateLimiter(st)
+    rng = np.random.default_rng(17)
+    sample = np.unique(rng.integers(0, n_keys, 20_000).astype(np.uint64))
+    sub_rows, sub_res = [], []
+    req = np.empty(TICK, tc.REQ_DTYPE)
+    for a in range(0, n_keys, TICK):                       # warm pass: one q=1 request per key at T0
+        ids = np.arange(a, min(a + TICK, n_keys), dtype=np.uint64)
+        w = np.zeros(len(ids), traces.REQ_DTYPE)
+        w["key"] = ids
+        traces.fill_policy(w, (ids % np.uint64(8)).astype(np.int64))
+        w["quantity"] = 1
+        w["now_ns"] = traces.T0
+        r = req[:len(ids)]
+        r["key_hash"] = tc.hash_key_ids(ids)
+        for f in ("max_burst", "count_per_period", "period", "quantity", "now_ns"):
+            r[f] = w[f]
+        out = lim.rate_limit_batch(r)
+        m = np.isin(ids, sample)
+        sub_rows.append(w[m])
+        sub_res.append(out[m].copy())
+    assert st.len() == n_keys
+    body = traces.config3(n_keys=n_keys, n_ticks=n_ticks, tick_size=TICK)
+    for t in range(n_ticks):
+        sl = body[t * TICK:(t + 1) * TICK]
+        req["key_hash"] = tc.hash_key_ids(sl["key"])
+        for f in ("max_burst", "count_per_period", "period", "quantity", "now_ns"):
+            req[f] = sl[f]
+        out = lim.rate_limit_batch(req)
+        m = np.isin(sl["key"], sample)
+        sub_rows.append(sl[m])
+        sub_res.append(out[m].copy())
+    sub = np.concatenate(sub_rows)
+    got = np.concatenate(sub_res)
+    want = oracle.OracleStore(oracle.PERIODIC, capacity=len(sample) * 2, created_ns=traces.T0, p0=10**9).replay(sub)
+    bad = first_mismatch(want, got, sub)
+    assert bad is None, bad
+    assert len(sub) > len(sample)
+    s = st.stats()
+    assert s["allowed"] + s["denied"] + s["errors"] == n_keys + n_ticks * TICK
+    # expiry of a key touched only by the warm pass = T0 + dvt(policy): P6 0 s, P5 0.5 s, P2 5.4 s, P0 5.94 s, ...
+    # keys touched by a tick moved on; count what the oracle semantics say is expired at T0 + 1 s among the sample,
+    # and for the whole table compare with the engine's own len bookkeeping
+    before = st.len()
+    removed = st.sweep(traces.T0 + 1_000_000_000)
+    assert 0.20 * n_keys < removed < 0.26 * n_keys          # P6 and P5 keys (2/8), minus those refreshed by a tick
+    assert st.len() == before - removed
+    assert st.sweep(traces.T0 + 1_000_000_000) == 0
+    rest = st.sweep(traces.T0 + 10**13)
+    assert rest == before - removed and st.len() == 0
+    st.close()

@@ -16,7 +16,7 @@ _SRC = os.path.join(_PKG, "csrc")
 SO_PATH = os.environ.get("GCRA_SO") or os.path.join(_PKG, "libgcra_b200.so")   # GCRA_SO: tuning variants
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "--shared", "-Xcompiler", "-fPIC", "-ldl"]
+              "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-ldl"]
 
 REQ_DTYPE = np.dtype([("key_hash", "<u8"), ("max_burst", "<i8"), ("count_per_period", "<i8"),
                       ("period", "<i8"), ("quantity", "<i8"), ("now_ns", "<i8")])
@@ -108,6 +108,18 @@ SYMBOLS = {
     "gcra_shard_submit": (_i32, [_vp, _u64, _vp, _vp, _vp]),
     "gcra_shard_join": (_i32, [_vp, _vp]),
     "gcra_shard_wait_tick": (_i32, [_vp, _u32, _vp]),
+    "gcra_p2p_prepare": (_i32, [_vp, _i32, _i32, _u32, _vp, C.POINTER(_vp)]),
+    "gcra_p2p_connect": (_i32, [_vp, _vp, _vp]),
+    "gcra_p2p_submit": (_i32, [_vp, _u64, _vp, _vp, _vp]),
+    "gcra_p2p_submit_route": (_i32, [_vp, _u64, _vp, _vp]),
+    "gcra_p2p_submit_finish": (_i32, [_vp, _vp]),
+    "gcra_p2p_wait_tick": (_i32, [_vp, _u32, _vp]),
+    "gcra_p2p_join": (_i32, [_vp, _vp]),
+    "gcra_p2p_error": (_i32, [_vp, C.POINTER(_u32)]),
+    "gcra_actor_create": (_i32, [_vp, _u32, _u32, C.POINTER(_vp)]),
+    "gcra_actor_throttle": (_i32, [_vp, C.c_char_p, _u64, _i64, _i64, _i64, _i64, _i64, _vp]),
+    "gcra_actor_stats": (_i32, [_vp, C.POINTER(_u64 * 3)]),
+    "gcra_actor_destroy": (None, [_vp]),
     "gcra_owner_of": (_u32, [_u64, _u32]),
     "gcra_route_partition": (_i32, [_vp, _u64, _vp, _u32, _vp, _vp, _vp, _vp]),
     "gcra_route_unpermute": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp]),

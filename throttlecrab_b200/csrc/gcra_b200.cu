@@ -17,6 +17,7 @@
 
 #include "gcra_kernels.cuh"
 #include "gcra_index_path.cuh"
+#include "gcra_p2p.cuh"
 
 using namespace gcra;
 
@@ -120,6 +121,31 @@ struct Shard {
     cudaEvent_t ev_tmp = nullptr;
 };
 
+// ---- multi-GPU over NVLink peer memory (gcra_p2p.cuh) ------------------------------------------------------
+struct P2PSlot {
+    u32 *res_loc = nullptr;            // [cap] where the result of my row i arrives in my outbox
+    u32 *counts_dev = nullptr;         // [world] rows I routed to every owner in this tick
+    SegDesc *segs_dev = nullptr;       // [world] segment r of this inbox slot: sender r's rows, sender r's outbox
+    cudaEvent_t ev_ready = nullptr, ev_wait = nullptr, ev_done = nullptr;
+    bool used = false;
+    uint32_t n = 0;
+};
+
+struct P2P {
+    int rank = 0, world = 0;
+    uint32_t cap = 0, cap_shift = 0;
+    void *window = nullptr;
+    size_t window_bytes = 0, inbox_off = 0, outbox_off = 0;
+    void *peer_base[P2P_MAX_WORLD] = {};
+    bool opened[P2P_MAX_WORLD] = {};
+    bool connected = false, routed_pending = false;
+    P2PPeers *peers_dev = nullptr;
+    u32 *tile_counts = nullptr;
+    cudaStream_t s_part = nullptr, s_wait = nullptr, s_sig = nullptr, s_return = nullptr;
+    P2PSlot slots[P2P_DEPTH];
+    uint64_t next_tick = 0;
+};
+
 // per-batch scratch; several sets so that the front halves of the next batches can overlap the back half of
 // the current one
 struct Scratch {
@@ -196,6 +222,7 @@ struct gcra_engine {
     uint64_t seen_allowed = 0, seen_expired_hits = 0;
     uint64_t n_sweeps = 0, n_grows = 0, n_purges = 0;
     Shard *shard = nullptr;          // multi-GPU: native NCCL pipeline (gcra_shard_*)
+    P2P *p2p = nullptr;              // multi-GPU: NVLink peer-memory pipeline (gcra_p2p_*)
     // index-order pipeline
     uint32_t epoch = 0;              // batch epoch of the slot marks (never 0)
     uint32_t bm_mask = 0;            // bitmap entries - 1
@@ -652,14 +679,14 @@ static int enqueue_mid_index(gcra_engine *h, Scratch &sc, Scratch &next, const B
                                                                  sc.bitmap, sc.pend, h->bm_mask, sc.flags, h->epoch, hp, h->dbg);
         resolve_kernel<true><<<rgrid, TILE_THREADS, 0, st>>>(h->tab, v, h->d_pol, h->npol, now_batch, sc.slot_arr,
                                                              h->bm_mask, sc.flags, h->epoch, ctrl, status, sc.keys_a,
-                                                             next.pend, sc.h_nres);
+                                                             next.pend, sc.h_nres, h->max_batch);
     } else {
         decide_index_kernel<false><<<grid, TILE_THREADS, 0, st>>>(h->tab, v, nullptr, 0, 0, sc.slot_arr, sc.bitmap, sc.pend,
                                                                   h->bm_mask, sc.flags, h->epoch, hp, h->dbg);
         if (timed) CK(cudaEventRecord(h->evd[3], st));
         resolve_kernel<false><<<rgrid, TILE_THREADS, 0, st>>>(h->tab, v, nullptr, 0, 0, sc.slot_arr, h->bm_mask,
                                                               sc.flags, h->epoch, ctrl, status, sc.keys_a,
-                                                              next.pend, sc.h_nres);
+                                                              next.pend, sc.h_nres, h->max_batch);
     }
     h->launches += 2;
     h->n_index_batches++;
@@ -854,6 +881,29 @@ static int launch_pipelined(gcra_engine *h, uint32_t n, const void *d_req, bool 
     return launch_pipelined_view(h, single_view(d_req, d_res, n), n, compact, now_batch, ready, done);
 }
 
+// CUDA loads a kernel's code lazily, at its FIRST launch, and that load may wait for running kernels.  The
+// multi-GPU pipelines keep kernels running that wait for work other launches deliver (flags in peer memory), so a
+// first launch behind such a kernel would stall until the wait gives up: load everything when the engine is made.
+template <typename K>
+static void preload(K kernel) {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, kernel);
+}
+
+static void preload_kernels() {
+    preload(ingest_kernel<false>); preload(ingest_kernel<true>);
+    preload(small_batch_kernel<false>); preload(small_batch_kernel<true>);
+    preload(sort_hist_kernel); preload(sort_rowscan_kernel); preload(sort_scatter_kernel); preload(sort_pass_fused_kernel);
+    preload(decide_kernel); preload(decide_runs_kernel<1>); preload(decide_runs_kernel<CLUSTER_CTAS>);
+    preload(probe_kernel<false>); preload(probe_kernel<true>);
+    preload(decide_index_kernel<false>); preload(decide_index_kernel<true>);
+    preload(resolve_kernel<false>); preload(resolve_kernel<true>);
+    preload(sweep_kernel); preload(purge_kernel); preload(clear_slots_kernel); preload(rehash_kernel); preload(store_op_kernel);
+    preload(route_count_kernel); preload(route_scan_kernel); preload(route_scatter_kernel); preload(route_unpermute_kernel);
+    preload(p2p_scan_kernel); preload(p2p_scatter_kernel); preload(p2p_signal_req_kernel); preload(p2p_signal_res_kernel);
+    preload(p2p_wait_kernel); preload(p2p_unpermute_kernel);
+}
+
 // ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
@@ -973,6 +1023,7 @@ int32_t gcra_create(const gcra_config *cfg, gcra_engine **out) {
         h->cur_interval = 5 * NS_PER_S;
         h->next_cleanup = created + 5 * NS_PER_S;
     }
+    preload_kernels();
     if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return fail("init", e);
     *out = h;
     return GCRA_OK;
@@ -992,6 +1043,17 @@ void gcra_destroy(gcra_engine *h) {
         if (nccl_rt::g_api.CommDestroy) { nccl_rt::g_api.CommDestroy(sh->comm_counts); nccl_rt::g_api.CommDestroy(sh->comm_req); nccl_rt::g_api.CommDestroy(sh->comm_res); }
         cudaStreamDestroy(sh->s_part); cudaStreamDestroy(sh->s_route); cudaStreamDestroy(sh->s_return); cudaEventDestroy(sh->ev_tmp);
         delete sh;
+    }
+    if (h->p2p) {
+        P2P *p = h->p2p;
+        for (int r = 0; r < p->world; r++) if (p->opened[r]) cudaIpcCloseMemHandle(p->peer_base[r]);
+        for (auto &sl : p->slots) {
+            cudaFree(sl.res_loc); cudaFree(sl.counts_dev); cudaFree(sl.segs_dev);
+            cudaEventDestroy(sl.ev_ready); cudaEventDestroy(sl.ev_wait); cudaEventDestroy(sl.ev_done);
+        }
+        cudaFree(p->peers_dev); cudaFree(p->tile_counts); cudaFree(p->window);
+        cudaStreamDestroy(p->s_part); cudaStreamDestroy(p->s_wait); cudaStreamDestroy(p->s_sig); cudaStreamDestroy(p->s_return);
+        delete p;
     }
     for (auto &s : h->ring) {
         cudaFreeHost(s.h_req); cudaFreeHost(s.h_res); cudaFree(s.d_req); cudaFree(s.d_res);
@@ -1613,6 +1675,210 @@ int32_t gcra_shard_join(gcra_engine *h, void *stream) {
     return GCRA_OK;
 }
 
+
+// ---- multi-GPU over NVLink peer memory: the whole sharded tick without NCCL and without a host sync ------------
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int32_t gcra_p2p_prepare(gcra_engine *h, int32_t rank, int32_t world, uint32_t cap_rows, void *ipc_handle_out_64,
+                         void **window_out) {
+    CK(cudaSetDevice(h->device));
+    if (h->p2p) { h->err = "p2p already prepared"; return GCRA_INTERNAL; }
+    if (world < 1 || world > P2P_MAX_WORLD || rank < 0 || rank >= world) { h->err = "bad rank / world"; return GCRA_INTERNAL; }
+    if (cap_rows == 0 || cap_rows > (1u << 24)) { h->err = "cap_rows must be in 1..2^24"; return GCRA_INTERNAL; }
+    P2P *p = new P2P();
+    p->rank = rank; p->world = world;
+    p->cap_shift = std::max<uint32_t>(ceil_log2(cap_rows), 10);      // whole resolve tiles per segment
+    p->cap = 1u << p->cap_shift;
+    if (((uint64_t)world << p->cap_shift) >= (1ULL << 31)) { delete p; h->err = "world * cap_rows too large"; return GCRA_INTERNAL; }
+    const size_t seg_rows = (size_t)P2P_DEPTH * world * p->cap;
+    p->inbox_off = align_up(sizeof(P2PHeader), 256);
+    p->outbox_off = align_up(p->inbox_off + seg_rows * sizeof(gcra_request), 256);
+    p->window_bytes = align_up(p->outbox_off + seg_rows * sizeof(gcra_result), 256);
+    CK(cudaMalloc(&p->window, p->window_bytes));
+    CK(cudaMemset(p->window, 0, p->inbox_off));
+    if (ipc_handle_out_64) {
+        cudaIpcMemHandle_t hd;
+        CK(cudaIpcGetMemHandle(&hd, p->window));
+        static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        memcpy(ipc_handle_out_64, &hd, 64);
+    }
+    if (window_out) *window_out = p->window;
+    CK(cudaStreamCreateWithFlags(&p->s_part, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&p->s_wait, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&p->s_sig, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&p->s_return, cudaStreamNonBlocking));
+    CK(cudaMalloc(&p->peers_dev, sizeof(P2PPeers)));
+    CK(cudaMalloc(&p->tile_counts, (size_t)ROUTE_MAX_SHARDS * ((p->cap + TILE_THREADS - 1) / TILE_THREADS) * sizeof(u32)));
+    for (auto &sl : p->slots) {
+        CK(cudaMalloc(&sl.res_loc, (size_t)p->cap * sizeof(u32)));
+        CK(cudaMalloc(&sl.counts_dev, P2P_MAX_WORLD * sizeof(u32)));
+        CK(cudaMalloc(&sl.segs_dev, P2P_MAX_WORLD * sizeof(SegDesc)));
+        CK(cudaEventCreateWithFlags(&sl.ev_ready, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&sl.ev_wait, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+    }
+    // the engine's per-row buffers now span the row-id space of a whole inbox slot
+    CK(cudaDeviceSynchronize());
+    for (auto &sc : h->scr) RC(alloc_index_scratch(h, sc, (uint32_t)world << p->cap_shift));
+    h->p2p = p;
+    return GCRA_OK;
+}
+
+// every rank's window: `ipc_handles` (world x 64 bytes, other processes) or `windows` (world pointers valid in THIS
+// process: engines that share a process, e.g. the single-GPU loop-back test)
+int32_t gcra_p2p_connect(gcra_engine *h, const void *ipc_handles, void *const *windows) {
+    CK(cudaSetDevice(h->device));
+    P2P *p = h->p2p;
+    if (!p) { h->err = "gcra_p2p_prepare first"; return GCRA_INTERNAL; }
+    if (!ipc_handles && !windows) { h->err = "need ipc handles or window pointers"; return GCRA_INTERNAL; }
+    P2PPeers peers{};
+    for (int r = 0; r < p->world; r++) {
+        void *base = nullptr;
+        if (r == p->rank) base = p->window;
+        else if (windows) base = windows[r];
+        else {
+            cudaIpcMemHandle_t hd;
+            memcpy(&hd, (const char *)ipc_handles + 64 * r, 64);
+            CK(cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess));
+            p->opened[r] = true;
+        }
+        p->peer_base[r] = base;
+        peers.hdr[r] = (P2PHeader *)base;
+        peers.inbox[r] = (unsigned char *)base + p->inbox_off;
+        peers.outbox[r] = (unsigned char *)base + p->outbox_off;
+    }
+    CK(cudaMemcpy(p->peers_dev, &peers, sizeof(peers), cudaMemcpyHostToDevice));
+    for (int d = 0; d < P2P_DEPTH; d++) {
+        SegDesc segs[P2P_MAX_WORLD] = {};
+        for (int r = 0; r < p->world; r++) {
+            // segment r of MY inbox slot d holds sender r's rows; their results go to slot d, segment `rank` of
+            // sender r's outbox
+            segs[r].req = peers.inbox[p->rank] + (((size_t)d * p->world + r) << p->cap_shift) * sizeof(gcra_request);
+            segs[r].res = (gcra_result *)(peers.outbox[r] + (((size_t)d * p->world + p->rank) << p->cap_shift) * sizeof(gcra_result));
+        }
+        CK(cudaMemcpy(p->slots[d].segs_dev, segs, sizeof(segs), cudaMemcpyHostToDevice));
+    }
+    p->connected = true;
+    return GCRA_OK;
+}
+
+// first half of a tick: the sender's side (partition + transfer + flags)
+int32_t gcra_p2p_submit_route(gcra_engine *h, uint64_t n64, const gcra_request *d_req, void *ready_stream) {
+    CK(cudaSetDevice(h->device));
+    P2P *p = h->p2p;
+    if (!p || !p->connected) { h->err = "gcra_p2p_prepare / gcra_p2p_connect first"; return GCRA_INTERNAL; }
+    if (p->routed_pending) { h->err = "gcra_p2p_submit_finish the previous tick first"; return GCRA_INTERNAL; }
+    if (n64 > p->cap) { h->err = "tick larger than cap_rows"; return GCRA_INTERNAL; }
+    const uint32_t n = (uint32_t)n64;
+    const uint32_t W = (uint32_t)p->world, me = (uint32_t)p->rank;
+    const uint64_t tick = ++p->next_tick;
+    const uint32_t d = (uint32_t)((tick - 1) % P2P_DEPTH);
+    P2PSlot &sl = p->slots[d];
+    // slot d again: its previous tick has been un-permuted here, i.e. every owner is through with my rows of that
+    // tick and with my outbox slot
+    if (sl.used) CK(cudaStreamWaitEvent(p->s_part, sl.ev_done, 0));
+    sl.used = true; sl.n = n;
+    if (ready_stream) {
+        CK(cudaEventRecord(sl.ev_ready, (cudaStream_t)ready_stream));
+        CK(cudaStreamWaitEvent(p->s_part, sl.ev_ready, 0));
+    }
+    // stable partition by owner, rows stored straight into the owners' inboxes, then the flags
+    const uint32_t tiles = (n + TILE_THREADS - 1) / TILE_THREADS;
+    if (n) {
+        route_count_kernel<<<tiles, TILE_THREADS, 0, p->s_part>>>(d_req, n, W, tiles, p->tile_counts);
+        p2p_scan_kernel<<<W, TILE_THREADS, 0, p->s_part>>>(p->tile_counts, tiles, sl.counts_dev);
+        p2p_scatter_kernel<<<tiles, TILE_THREADS, 0, p->s_part>>>(d_req, n, W, me, d, p->cap_shift, tiles, p->tile_counts,
+                                                                 p->peers_dev, sl.res_loc);
+        h->launches += 3;
+    } else {
+        CK(cudaMemsetAsync(sl.counts_dev, 0, W * sizeof(u32), p->s_part));
+    }
+    p2p_signal_req_kernel<<<1, 32, 0, p->s_part>>>(p->peers_dev, sl.counts_dev, W, me, d, tick);
+    h->launches++;
+    CK(cudaGetLastError());
+    p->routed_pending = true;
+    return GCRA_OK;
+}
+
+// second half: the owner's side (wait for every sender, decide, results into the senders' outboxes, flags) and the
+// way back (wait for every owner, results into input order)
+int32_t gcra_p2p_submit_finish(gcra_engine *h, gcra_result *d_res) {
+    CK(cudaSetDevice(h->device));
+    P2P *p = h->p2p;
+    if (!p || !p->routed_pending) { h->err = "gcra_p2p_submit_route first"; return GCRA_INTERNAL; }
+    p->routed_pending = false;
+    const uint32_t W = (uint32_t)p->world, me = (uint32_t)p->rank;
+    const uint64_t tick = p->next_tick;
+    const uint32_t d = (uint32_t)((tick - 1) % P2P_DEPTH);
+    P2PSlot &sl = p->slots[d];
+    P2PHeader *hdr = (P2PHeader *)p->window;
+    // owner: wait for every sender's rows of this tick, then the engine over the inbox slot as one batch of W
+    // segments (row counts in the header); its kernels store the results into the senders' outboxes
+    p2p_wait_kernel<<<1, 32, 0, p->s_wait>>>(hdr, 0, W, tick);
+    CK(cudaEventRecord(sl.ev_wait, p->s_wait));
+    BatchView v{};
+    v.req0 = nullptr; v.res0 = nullptr;
+    v.segs = sl.segs_dev;
+    v.dev_counts = &hdr->counts[d][0];
+    v.n = 0;
+    v.nseg = W;
+    v.cap_shift = p->cap_shift;
+    cudaEvent_t done = nullptr;
+    const uint32_t n_rows = (uint32_t)std::min<uint64_t>((uint64_t)W << p->cap_shift, h->max_batch);
+    RC(launch_pipelined_view(h, v, n_rows, false, 0, sl.ev_wait, &done));
+    CK(cudaStreamWaitEvent(p->s_sig, done, 0));
+    p2p_signal_res_kernel<<<1, 32, 0, p->s_sig>>>(p->peers_dev, W, me, tick);
+    // sender again: every owner's results of this tick are in my outbox -> input order, into the caller's buffer
+    p2p_wait_kernel<<<1, 32, 0, p->s_return>>>(hdr, 1, W, tick);
+    if (sl.n) {
+        const uint32_t tiles = (sl.n + TILE_THREADS - 1) / TILE_THREADS;
+        p2p_unpermute_kernel<<<tiles, TILE_THREADS, 0, p->s_return>>>((const unsigned char *)p->window + p->outbox_off, sl.res_loc,
+                                                                     sl.n, W, d, p->cap_shift, d_res);
+        h->launches++;
+    }
+    CK(cudaEventRecord(sl.ev_done, p->s_return));
+    h->launches += 3;
+    CK(cudaGetLastError());
+    return GCRA_OK;
+}
+
+int32_t gcra_p2p_submit(gcra_engine *h, uint64_t n, const gcra_request *d_req, gcra_result *d_res, void *ready_stream) {
+    RC(gcra_p2p_submit_route(h, n, d_req, ready_stream));
+    return gcra_p2p_submit_finish(h, d_res);
+}
+
+// make `stream` wait for the results of the tick submitted `ticks_back` submissions ago (0 = the latest, < DEPTH)
+int32_t gcra_p2p_wait_tick(gcra_engine *h, uint32_t ticks_back, void *stream) {
+    CK(cudaSetDevice(h->device));
+    P2P *p = h->p2p;
+    if (!p || ticks_back >= (uint32_t)P2P_DEPTH || ticks_back >= p->next_tick) { h->err = "bad tick"; return GCRA_INTERNAL; }
+    P2PSlot &sl = p->slots[(p->next_tick - 1 - ticks_back) % P2P_DEPTH];
+    if (stream) CK(cudaStreamWaitEvent((cudaStream_t)stream, sl.ev_done, 0));
+    else CK(cudaEventSynchronize(sl.ev_done));
+    return GCRA_OK;
+}
+
+int32_t gcra_p2p_join(gcra_engine *h, void *stream) {
+    CK(cudaSetDevice(h->device));
+    P2P *p = h->p2p;
+    if (!p) { h->err = "gcra_p2p_prepare first"; return GCRA_INTERNAL; }
+    for (auto &sl : p->slots) {
+        if (!sl.used) continue;
+        if (stream) CK(cudaStreamWaitEvent((cudaStream_t)stream, sl.ev_done, 0));
+        else CK(cudaEventSynchronize(sl.ev_done));
+    }
+    return GCRA_OK;
+}
+
+// 1 when a wait on this rank gave up (a peer never delivered a tick): results since then are not to be trusted
+int32_t gcra_p2p_error(gcra_engine *h, uint32_t *error) {
+    CK(cudaSetDevice(h->device));
+    P2P *p = h->p2p;
+    if (!p) { h->err = "gcra_p2p_prepare first"; return GCRA_INTERNAL; }
+    CK(cudaMemcpy(error, (const char *)p->window + offsetof(P2PHeader, error), sizeof(u32), cudaMemcpyDeviceToHost));
+    return GCRA_OK;
+}
+
 // ---- routing -------------------------------------------------------------------------------------
 uint32_t gcra_owner_of(uint64_t key_hash, uint32_t n_shards) { return owner_of(key_hash, n_shards); }
 
@@ -1644,3 +1910,5 @@ int32_t gcra_route_unpermute(gcra_engine *h, uint64_t n, const gcra_result *d_re
 }
 
 }  // extern "C"
+
+#include "gcra_actor.inc"

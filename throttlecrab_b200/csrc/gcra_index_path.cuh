@@ -429,7 +429,7 @@ resolve_kernel(Table t, BatchView b, const PolicyDerived *__restrict__ pol, u32 
                const u32 *__restrict__ slot_arr, u32 bm_mask,
                const unsigned char *__restrict__ flags, u32 epoch, u32 *__restrict__ ctrl,
                volatile u64 *__restrict__ tile_status, u64 *__restrict__ res_keys,
-               u32 *__restrict__ next_pend, volatile u32 *__restrict__ host_nres) {
+               u32 *__restrict__ next_pend, volatile u32 *__restrict__ host_nres, u32 res_cap) {
     constexpr u32 RSZ = COMPACT ? sizeof(gcra_request16) : sizeof(gcra_request);
     __shared__ u32 part[TILE_THREADS / 32];
     __shared__ u32 sm_tile, sm_base;
@@ -509,8 +509,8 @@ resolve_kernel(Table t, BatchView b, const PolicyDerived *__restrict__ pol, u32 
                 sm_base = base;
                 u32 r0, c0;
                 if (!res_tile_lookup(b, tile + 1, r0, c0)) {                // last tile: residue size
-                    ctrl[RC_NRES] = base + total;
-                    *host_nres = base + total;                              // mapped pinned host memory: feedback for the host
+                    ctrl[RC_NRES] = min(base + total, res_cap);
+                    *host_nres = min(base + total, res_cap);                // mapped pinned host memory: feedback for the host
                 }
             }
         }
@@ -521,6 +521,13 @@ resolve_kernel(Table t, BatchView b, const PolicyDerived *__restrict__ pol, u32 
             if (!residue[k]) continue;
             const u32 row = first_row + k;
             const u32 p = base + rank++;
+            if (p >= res_cap) {
+                // more residue than the engine's batch capacity (a multi-GPU tick far beyond max_batch): the row
+                // is answered with an internal error instead of overrunning the sort buffers
+                write_result(b.res_at(row), 0, 0, 0, GCRA_INTERNAL, 0);
+                atomicAdd(&t.counters[C_ERRORS], 1ULL);
+                continue;
+            }
             res_keys[p] = ((u64)slot[k] << 32) | row;     // the tail parses the request of row `row` itself
             // the next batch must keep off this key until this batch's tail is through with it
             const u32 e = slot[k] & bm_mask;

@@ -233,3 +233,84 @@ class NativeShardedLimiter:
     def step(self, d_req, d_res):
         self.submit(d_req, d_res)
         self.finish()
+
+    def describe(self):
+        return "native NCCL pipeline (gcra_shard_submit: partition, count exchange, all-to-all, decide, all-to-all)"
+
+
+class PeerShardedLimiter:
+    """The sharded tick over NVLink peer memory (gcra_p2p_*, csrc/gcra_p2p.cuh): the partition kernel stores every
+    request row straight into its owner's inbox, the owner's engine runs over the inbox as one batch of `world`
+    segments and stores every result straight into the sender's outbox; ranks synchronise with tick numbers in peer
+    memory.  No NCCL in the data path, no host synchronisation.  torch.distributed is used once, to all-gather the
+    64-byte CUDA IPC handles of the ranks' windows."""
+
+    def __init__(self, limiter, dist, device, max_rows=None):
+        import ctypes as C
+        self.lim, self.dist, self.dev = limiter, dist, device
+        self.L, self.h = limiter._L, limiter._h
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.cap = max_rows or limiter.store.max_batch
+        buf = (C.c_char * 64)()
+        win = C.c_void_p()
+        limiter.store._check(self.L.gcra_p2p_prepare(self.h, self.rank, self.world, self.cap, C.addressof(buf), C.byref(win)))
+        mine = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone().to(device)
+        allh = [torch.zeros(64, dtype=torch.uint8, device=device) for _ in range(self.world)]
+        dist.all_gather(allh, mine)
+        raw = b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh)
+        limiter.store._check(self.L.gcra_p2p_connect(self.h, raw, None))
+        dist.barrier()                       # every window is mapped everywhere before the first row is stored
+        self.n_submitted = 0
+
+    def submit(self, d_req, d_res, ready_stream=None):
+        n = d_req.numel() // REQ_B
+        st = ready_stream if ready_stream is not None else torch.cuda.current_stream(self.dev).cuda_stream
+        self.lim.store._check(self.L.gcra_p2p_submit(self.h, n, d_req.data_ptr(), d_res.data_ptr(), st))
+        self.n_submitted += 1
+
+    def wait_tick(self, ticks_back, stream):
+        self.lim.store._check(self.L.gcra_p2p_wait_tick(self.h, ticks_back, stream.cuda_stream))
+
+    def finish(self):
+        self.lim.store._check(self.L.gcra_p2p_join(self.h, torch.cuda.current_stream(self.dev).cuda_stream))
+
+    def step(self, d_req, d_res):
+        self.submit(d_req, d_res)
+        self.finish()
+
+    def error(self):
+        import ctypes as C
+        e = C.c_uint32()
+        self.lim.store._check(self.L.gcra_p2p_error(self.h, C.byref(e)))
+        return int(e.value)
+
+    def describe(self):
+        return ("NVLink peer memory (gcra_p2p_submit: partition kernel stores rows into the owners' inboxes, owners store "
+                "results into the senders' outboxes, flags in peer memory; no NCCL, no host sync)")
+
+
+def connect_local(limiters, cap_rows):
+    """Engines that live in ONE process (the single-GPU loop-back test): windows are exchanged as plain pointers."""
+    import ctypes as C
+    world = len(limiters)
+    wins = (C.c_void_p * world)()
+    for r, lim in enumerate(limiters):
+        w = C.c_void_p()
+        lim.store._check(lim._L.gcra_p2p_prepare(lim._h, r, world, cap_rows, None, C.byref(w)))
+        wins[r] = w.value
+    for lim in limiters:
+        lim.store._check(lim._L.gcra_p2p_connect(lim._h, None, wins))
+
+
+def make_sharded(limiter, dist, device, max_rows=None):
+    """The sharded pipeline bench.py and the tests use: NVLink peer-memory routing (gcra_p2p_*) when the ranks can
+    map each other's memory, else the NCCL pipeline.  GCRA_SHARD=nccl / p2p forces one."""
+    import os
+    want = os.environ.get("GCRA_SHARD", "auto")
+    if want != "nccl" and "PeerShardedLimiter" in globals():
+        try:
+            return PeerShardedLimiter(limiter, dist, device, max_rows)
+        except Exception:
+            if want == "p2p":
+                raise
+    return NativeShardedLimiter(limiter, dist, device, max_rows)
