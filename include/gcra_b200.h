@@ -46,6 +46,8 @@ enum {
  * INDEX_PATH forces the first for every batch above 255 requests, SORT_PATH disables it. */
 #define GCRA_FLAG_INDEX_PATH 2u
 #define GCRA_FLAG_SORT_PATH 4u
+/* draw the key-hash seed from /dev/urandom (see "key identity" below); overrides gcra_config.hash_seed */
+#define GCRA_FLAG_RANDOM_SEED 8u
 
 typedef struct gcra_engine gcra_engine;
 
@@ -57,6 +59,7 @@ typedef struct {
     int64_t created_ns;   /* stands in for SystemTime::now() in the constructors (adaptive_cleanup.rs:94) */
     uint32_t max_batch;   /* largest number of requests one kernel pass carries (0 -> 1<<20) */
     uint32_t flags;       /* GCRA_FLAG_* */
+    uint64_t hash_seed[2]; /* SipHash key of the string-keyed entry points; (0,0) = the unkeyed gcra_hash_key */
 } gcra_config;
 
 /* One call of RateLimiter::rate_limit(key, max_burst, count_per_period, period, quantity, now)
@@ -116,8 +119,20 @@ void gcra_destroy(gcra_engine *h);
 const char *gcra_last_error(gcra_engine *h);
 
 /* ---- host helpers (no device work) ---------------------------------------------------- */
-/* the key -> 64-bit identity the table stores instead of the String key (adaptive_cleanup.rs:40) */
+/* KEY IDENTITY.  The reference keeps the key String in its map and compares it (adaptive_cleanup.rs:40, a randomly
+ * seeded AHashMap).  This table identifies a key by a 64-bit hash ONLY: two keys with the same hash share one entry
+ * (one quota).  Among n honest keys that happens with probability ~n^2 / 2^65 (10^8 keys: ~3 * 10^-4).  But
+ * gcra_hash_key is UNKEYED and every step of it is invertible: whoever chooses key bytes can construct a key that
+ * collides with a victim's, or keys that fill one bucket pair and the stash ("table full" errors for others).  Where
+ * keys come from untrusted clients give the engine a secret seed (gcra_config.hash_seed, or GCRA_FLAG_RANDOM_SEED):
+ * the string-keyed entry points (gcra_rate_limit, gcra_store_*, gcra_actor_throttle) then hash with SipHash-2-4
+ * under that seed, and callers of the batch entry points fill gcra_request.key_hash with gcra_engine_hash_key (or
+ * gcra_hash_key_seeded and the seed, which gcra_get_hash_seed returns; a snapshot carries it; engines that shard one
+ * key space must share it).  gcra_hash_key stays for trusted / synthetic key universes (tests, benches). */
 uint64_t gcra_hash_key(const void *key, uint64_t len);
+uint64_t gcra_hash_key_seeded(const void *key, uint64_t len, uint64_t seed0, uint64_t seed1);
+uint64_t gcra_engine_hash_key(gcra_engine *h, const void *key, uint64_t len);
+void gcra_get_hash_seed(gcra_engine *h, uint64_t out[2]);
 /* hash n keys of the form "<prefix><decimal id>" (trace generation: "k:<i>") */
 void gcra_hash_key_ids(const void *prefix, uint64_t prefix_len, const uint64_t *ids, uint64_t n,
                        uint64_t *out);
@@ -180,6 +195,10 @@ int32_t gcra_ring_poll(gcra_engine *h, uint32_t slot, int32_t *done);
 /* ---- sweep and introspection ------------------------------------------------------------ */
 /* HashMap::retain(expiry > now) (adaptive_cleanup.rs:176-182), unconditionally */
 int32_t gcra_sweep(gcra_engine *h, int64_t now_ns, uint64_t *removed);
+/* the store kind's own policy (maybe_clean_expired) against the caller's clock: for callers of the device-resident,
+ * pipelined and sharded submissions, which -- unlike the host-buffer calls and the ring -- never sweep by themselves
+ * (the requests' clocks live on the device).  Waits for the submitted batches; *swept = entries removed. */
+int32_t gcra_policy_tick(gcra_engine *h, int64_t now_ns, uint64_t *swept);
 /* len() (periodic.rs:113-116) */
 uint64_t gcra_len(gcra_engine *h);
 int32_t gcra_get_stats(gcra_engine *h, gcra_stats *out);
@@ -255,6 +274,11 @@ int32_t gcra_p2p_submit_route(gcra_engine *h, uint64_t n, const gcra_request *d_
 int32_t gcra_p2p_submit_finish(gcra_engine *h, gcra_result *d_res);
 int32_t gcra_p2p_wait_tick(gcra_engine *h, uint32_t ticks_back, void *stream);
 int32_t gcra_p2p_join(gcra_engine *h, void *stream);
+/* stage times (ms) of the most recent tick submitted while timing was on; meaningful when ticks run one at a time:
+ * [0] partition + transfer + flags, [1] until every sender's rows are here, [2] the engine over the inbox,
+ * [3] until every owner's results are here, [4] un-permutation */
+int32_t gcra_p2p_set_timing(gcra_engine *h, int32_t on);
+int32_t gcra_p2p_last_tick_ms(gcra_engine *h, float out[5]);
 /* *error = 1 when a wait on this rank gave up after ~20 s (a peer never delivered a tick) */
 int32_t gcra_p2p_error(gcra_engine *h, uint32_t *error);
 

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts():
     assert tc.REQ_DTYPE.itemsize == 48 and tc.RES_DTYPE.itemsize == 32 and tc.REQ16_DTYPE.itemsize == 16
     assert tc.RES_DTYPE.fields["status"][1] == 24 and tc.RES_DTYPE.fields["allowed"][1] == 28
-    assert ctypes.sizeof(_native.Config) == 56
+    assert ctypes.sizeof(_native.Config) == 72      # ... + hash_seed[2]
 
 
 def test_derive_params_matches_oracle():
@@ -83,3 +83,15 @@ def test_rate_mirror_matches_reference_tests():
     assert tc.Rate.from_count_and_period(0, 60).period() == (2**64 - 1) * S
     assert tc.Rate.from_count_and_period(10, 0).period() == (2**64 - 1) * S
     assert tc.Rate.new(250_000_000).period() == 250_000_000
+
+
+def test_seeded_key_hash_is_siphash_2_4():
+    """gcra_hash_key_seeded = SipHash-2-4 (reference vectors of the SipHash paper's test program: key 00..0f, input
+    00, 01, ... of increasing length)."""
+    L = _native.lib()
+    k0, k1 = 0x0706050403020100, 0x0f0e0d0c0b0a0908
+    want = {0: 0x726fdb47dd0e0e31, 1: 0x74f839c593dc67fd, 8: 0x93f5f5799a932462, 15: 0xa129ca6149be45e5}
+    for n, w in want.items():
+        data = bytes(range(n))
+        assert L.gcra_hash_key_seeded(data, n, k0, k1) == w, n
+    assert L.gcra_hash_key_seeded(b"abc", 3, 1, 2) != L.gcra_hash_key_seeded(b"abc", 3, 1, 3)

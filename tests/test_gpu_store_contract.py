@@ -48,3 +48,33 @@ def test_no_cleanup_without_triggers():        # cleanup_test.rs:86-107
         st.get("key_%d" % i, NOW)
     assert st.len() == 100
     assert st.stats()["sweeps"] == 0
+
+
+@pytest.mark.parametrize("k1_path", ["auto"], indirect=True)
+def test_seeded_key_identity(k1_path, tmp_path):
+    """An engine with a hash seed identifies string keys with SipHash-2-4 under that seed (include/gcra_b200.h, "key
+    identity"): same decisions, other identities than the unkeyed hash, the seed survives a snapshot."""
+    import traces
+    seed = (0x1122334455667788, 0x99aabbccddeeff01)
+    st = tc.PeriodicStore(capacity=1000, created_ns=traces.T0, hash_seed=seed)
+    lim = tc.RateLimiter(st)
+    for i in range(5):
+        ok, r = lim.rate_limit("burst_test", 5, 10, 60, 1, traces.T0)          # core/tests.rs:17-33
+        assert ok and r.remaining == 4 - i
+    ok, r = lim.rate_limit("burst_test", 5, 10, 60, 1, traces.T0)
+    assert not ok
+    assert st.hash_seed() == seed
+    assert st.hash_key("burst_test") != tc.hash_key("burst_test")
+    assert st.peek(st.hash_key("burst_test")) is not None and st.peek(tc.hash_key("burst_test")) is None
+    assert st.get("burst_test", traces.T0) is not None
+    path = str(tmp_path / "seeded.snap")
+    st.save(path)
+    st2 = tc.PeriodicStore(capacity=1000, created_ns=traces.T0)               # no seed of its own
+    st2.load(path)
+    assert st2.hash_seed() == seed
+    ok, _ = tc.RateLimiter(st2).rate_limit("burst_test", 5, 10, 60, 1, traces.T0)
+    assert not ok                                                             # the same key, still exhausted
+    rnd = tc.PeriodicStore(capacity=1000, created_ns=traces.T0, flags=8)      # GCRA_FLAG_RANDOM_SEED
+    assert rnd.hash_seed() != (0, 0)
+    for s in (st, st2, rnd):
+        s.close()

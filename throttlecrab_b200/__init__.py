@@ -148,12 +148,12 @@ class _GpuStore:
     """A GPU-resident key -> (tat, expiry) table standing in for one reference store."""
     KIND = _native.STORE_ADAPTIVE
 
-    def __init__(self, capacity=1000, device=0, created_ns=None, p0=0, p1=0, p2=0, max_batch=0, flags=0):
+    def __init__(self, capacity=1000, device=0, created_ns=None, p0=0, p1=0, p2=0, max_batch=0, flags=0, hash_seed=(0, 0)):
         import time
         L = _native.lib()
         cfg = _native.Config(capacity=capacity, device=device, store_kind=self.KIND, p0=p0, p1=p1,
                              p2=p2, created_ns=time.time_ns() if created_ns is None else created_ns,
-                             max_batch=max_batch, flags=flags)
+                             max_batch=max_batch, flags=flags, hash_seed=(C.c_uint64 * 2)(*hash_seed))
         h = C.c_void_p()
         if L.gcra_create(C.byref(cfg), C.byref(h)) != OK or not h:
             raise RuntimeError("gcra_create failed: the CUDA engine is unavailable "
@@ -221,6 +221,23 @@ class _GpuStore:
         r = C.c_uint64()
         self._check(self._L.gcra_sweep(self._h, _ns(now), C.byref(r)))
         return r.value
+
+    def policy_tick(self, now):
+        """The store kind's sweep policy against the caller's clock (for device-resident / pipelined / sharded
+        submissions, which never sweep by themselves); returns the number of entries removed."""
+        r = C.c_uint64()
+        self._check(self._L.gcra_policy_tick(self._h, _ns(now), C.byref(r)))
+        return r.value
+
+    def hash_key(self, key):
+        """The identity THIS engine gives a key (SipHash-2-4 under the engine's seed when it has one)."""
+        k = _kb(key)
+        return int(self._L.gcra_engine_hash_key(self._h, k, len(k)))
+
+    def hash_seed(self):
+        out = (C.c_uint64 * 2)()
+        self._L.gcra_get_hash_seed(self._h, C.byref(out))
+        return int(out[0]), int(out[1])
 
     def peek(self, key_hash):
         t, e, f = C.c_int64(), C.c_int64(), C.c_uint8()

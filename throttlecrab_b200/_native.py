@@ -28,13 +28,14 @@ assert REQ_DTYPE.itemsize == 48 and RES_DTYPE.itemsize == 32 and REQ16_DTYPE.ite
 
 OK, NEGATIVE_QUANTITY, INVALID_RATE_LIMIT, INTERNAL = 0, 1, 2, 3
 STORE_PERIODIC, STORE_PROBABILISTIC, STORE_ADAPTIVE, STORE_MANUAL = 0, 1, 2, 3
-FLAG_TIGHT_TABLE, FLAG_INDEX_PATH, FLAG_SORT_PATH = 1, 2, 4
+FLAG_TIGHT_TABLE, FLAG_INDEX_PATH, FLAG_SORT_PATH, FLAG_RANDOM_SEED = 1, 2, 4, 8
 
 
 class Config(C.Structure):
     _fields_ = [("capacity", C.c_uint64), ("device", C.c_int32), ("store_kind", C.c_int32),
                 ("p0", C.c_uint64), ("p1", C.c_uint64), ("p2", C.c_uint64),
-                ("created_ns", C.c_int64), ("max_batch", C.c_uint32), ("flags", C.c_uint32)]
+                ("created_ns", C.c_int64), ("max_batch", C.c_uint32), ("flags", C.c_uint32),
+                ("hash_seed", C.c_uint64 * 2)]
 
 
 class Stats(C.Structure):
@@ -72,6 +73,9 @@ SYMBOLS = {
     "gcra_destroy": (None, [_vp]),
     "gcra_last_error": (C.c_char_p, [_vp]),
     "gcra_hash_key": (_u64, [C.c_char_p, _u64]),
+    "gcra_hash_key_seeded": (_u64, [C.c_char_p, _u64, _u64, _u64]),
+    "gcra_engine_hash_key": (_u64, [_vp, C.c_char_p, _u64]),
+    "gcra_get_hash_seed": (None, [_vp, C.POINTER(_u64 * 2)]),
     "gcra_hash_key_ids": (None, [C.c_char_p, _u64, _vp, _u64, _vp]),
     "gcra_derive_params": (_i32, [_i64, _i64, _i64, _pi64, _pi64]),
     "gcra_store_get": (_i32, [_vp, C.c_char_p, _u64, _i64, _pi64, _pu8]),
@@ -92,6 +96,7 @@ SYMBOLS = {
     "gcra_ring_wait": (_i32, [_vp, _u32]),
     "gcra_ring_poll": (_i32, [_vp, _u32, C.POINTER(_i32)]),
     "gcra_sweep": (_i32, [_vp, _i64, _pu64]),
+    "gcra_policy_tick": (_i32, [_vp, _i64, _pu64]),
     "gcra_len": (_u64, [_vp]),
     "gcra_get_stats": (_i32, [_vp, C.POINTER(Stats)]),
     "gcra_peek": (_i32, [_vp, _u64, _pi64, _pi64, _pu8]),
@@ -116,6 +121,8 @@ SYMBOLS = {
     "gcra_p2p_wait_tick": (_i32, [_vp, _u32, _vp]),
     "gcra_p2p_join": (_i32, [_vp, _vp]),
     "gcra_p2p_error": (_i32, [_vp, C.POINTER(_u32)]),
+    "gcra_p2p_set_timing": (_i32, [_vp, _i32]),
+    "gcra_p2p_last_tick_ms": (_i32, [_vp, C.POINTER(C.c_float * 5)]),
     "gcra_actor_create": (_i32, [_vp, _u32, _u32, C.POINTER(_vp)]),
     "gcra_actor_throttle": (_i32, [_vp, C.c_char_p, _u64, _i64, _i64, _i64, _i64, _i64, _vp]),
     "gcra_actor_stats": (_i32, [_vp, C.POINTER(_u64 * 3)]),

@@ -144,6 +144,8 @@ struct P2P {
     cudaStream_t s_part = nullptr, s_wait = nullptr, s_sig = nullptr, s_return = nullptr;
     P2PSlot slots[P2P_DEPTH];
     uint64_t next_tick = 0;
+    bool timed = false, timed_valid = false;
+    cudaEvent_t ev_t[6] = {};
 };
 
 // per-batch scratch; several sets so that the front halves of the next batches can overlap the back half of
@@ -242,6 +244,7 @@ struct gcra_engine {
     std::vector<RingSlot> ring;
     uint32_t ring_cap = 0;
     bool ring_compact = false;
+    uint64_t hash_seed[2] = {0, 0};  // SipHash key of the string-keyed entry points ((0,0): the unkeyed gcra_hash_key)
     std::string err;
 };
 
@@ -309,7 +312,8 @@ static int do_sweep(gcra_engine *h, int64_t now_ns, uint64_t *removed) {
     uint64_t before = h->h_counters[C_SWEPT];
     uint32_t grid = (uint32_t)std::min<uint64_t>(((uint64_t)h->total_lines * 2 + TILE_THREADS * SWEEP_UNROLL - 1) / (TILE_THREADS * SWEEP_UNROLL), 148 * 16);
     CK(cudaEventRecord(h->ev_sweep[0], h->stream));
-    sweep_kernel<<<grid, TILE_THREADS, 0, h->stream>>>(h->tab, (u64)h->total_lines * 4, now_ns);
+    static const int sweep_mode = getenv("GCRA_SWEEP_MODE") ? atoi(getenv("GCRA_SWEEP_MODE")) : 0;
+    sweep_kernel<<<grid, TILE_THREADS, 0, h->stream>>>(h->tab, (u64)h->total_lines * 4, now_ns, sweep_mode);
     CK(cudaEventRecord(h->ev_sweep[1], h->stream));
     h->sweep_timed = true;
     h->launches++;
@@ -940,6 +944,19 @@ int32_t gcra_create(const gcra_config *cfg, gcra_engine **out) {
     h->capacity = cfg->capacity ? cfg->capacity : 1000;      // DEFAULT_CAPACITY adaptive_cleanup.rs:10
     h->max_batch = cfg->max_batch ? cfg->max_batch : (1u << 20);
     h->tight = (cfg->flags & GCRA_FLAG_TIGHT_TABLE) != 0;
+    h->hash_seed[0] = cfg->hash_seed[0];
+    h->hash_seed[1] = cfg->hash_seed[1];
+    if (cfg->flags & GCRA_FLAG_RANDOM_SEED) {
+        FILE *ur = fopen("/dev/urandom", "rb");
+        if (!ur || fread(h->hash_seed, sizeof(h->hash_seed), 1, ur) != 1) {
+            if (ur) fclose(ur);
+            fprintf(stderr, "gcra_create: cannot read /dev/urandom for the hash seed\n");
+            delete h;
+            return GCRA_INTERNAL;
+        }
+        fclose(ur);
+        h->hash_seed[0] |= 1;      // never (0, 0)
+    }
     u64 *counters = nullptr;
     if ((e = cudaMalloc(&counters, C_COUNT * sizeof(u64))) != cudaSuccess) return fail("counters", e);
     cudaMemsetAsync(counters, 0, C_COUNT * sizeof(u64), h->stream);
@@ -1051,6 +1068,7 @@ void gcra_destroy(gcra_engine *h) {
             cudaFree(sl.res_loc); cudaFree(sl.counts_dev); cudaFree(sl.segs_dev);
             cudaEventDestroy(sl.ev_ready); cudaEventDestroy(sl.ev_wait); cudaEventDestroy(sl.ev_done);
         }
+        for (auto &e : p->ev_t) cudaEventDestroy(e);
         cudaFree(p->peers_dev); cudaFree(p->tile_counts); cudaFree(p->window);
         cudaStreamDestroy(p->s_part); cudaStreamDestroy(p->s_wait); cudaStreamDestroy(p->s_sig); cudaStreamDestroy(p->s_return);
         delete p;
@@ -1099,6 +1117,44 @@ uint64_t gcra_hash_key(const void *key, uint64_t len) {
     return mix64(hsh);
 }
 
+// SipHash-2-4 (Aumasson & Bernstein), 64-bit output: the keyed hash for keys an adversary may choose
+static inline uint64_t rotl64(uint64_t x, int b) { return (x << b) | (x >> (64 - b)); }
+uint64_t gcra_hash_key_seeded(const void *key, uint64_t len, uint64_t k0, uint64_t k1) {
+    uint64_t v0 = 0x736f6d6570736575ULL ^ k0, v1 = 0x646f72616e646f6dULL ^ k1;
+    uint64_t v2 = 0x6c7967656e657261ULL ^ k0, v3 = 0x7465646279746573ULL ^ k1;
+    const unsigned char *p = (const unsigned char *)key;
+    const unsigned char *end = p + (len & ~7ULL);
+#define GCRA_SIPROUND                                                                 \
+    do {                                                                              \
+        v0 += v1; v1 = rotl64(v1, 13); v1 ^= v0; v0 = rotl64(v0, 32);                \
+        v2 += v3; v3 = rotl64(v3, 16); v3 ^= v2;                                      \
+        v0 += v3; v3 = rotl64(v3, 21); v3 ^= v0;                                      \
+        v2 += v1; v1 = rotl64(v1, 17); v1 ^= v2; v2 = rotl64(v2, 32);                \
+    } while (0)
+    for (; p != end; p += 8) {
+        uint64_t m;
+        memcpy(&m, p, 8);
+        v3 ^= m; GCRA_SIPROUND; GCRA_SIPROUND; v0 ^= m;
+    }
+    uint64_t b = len << 56;
+    for (uint64_t i = 0; i < (len & 7); i++) b |= (uint64_t)p[i] << (8 * i);
+    v3 ^= b; GCRA_SIPROUND; GCRA_SIPROUND; v0 ^= b;
+    v2 ^= 0xff;
+    GCRA_SIPROUND; GCRA_SIPROUND; GCRA_SIPROUND; GCRA_SIPROUND;
+#undef GCRA_SIPROUND
+    return v0 ^ v1 ^ v2 ^ v3;
+}
+
+// the identity the engine's own string-keyed entry points give a key: keyed when the engine has a seed
+static uint64_t engine_hash(const gcra_engine *h, const void *key, uint64_t len) {
+    return (h->hash_seed[0] | h->hash_seed[1]) ? gcra_hash_key_seeded(key, len, h->hash_seed[0], h->hash_seed[1])
+                                               : gcra_hash_key(key, len);
+}
+
+uint64_t gcra_engine_hash_key(gcra_engine *h, const void *key, uint64_t len) { return engine_hash(h, key, len); }
+
+void gcra_get_hash_seed(gcra_engine *h, uint64_t out[2]) { out[0] = h->hash_seed[0]; out[1] = h->hash_seed[1]; }
+
 void gcra_hash_key_ids(const void *prefix, uint64_t prefix_len, const uint64_t *ids, uint64_t n, uint64_t *out) {
     char buf[96];
     if (prefix_len > 64) prefix_len = 64;
@@ -1126,6 +1182,9 @@ static int store_op(gcra_engine *h, int op, uint64_t key_hash, int64_t a, int64_
     // the table encodes 'no state' as a negative expiry: times before the epoch are outside its domain
     if (op != 3 && now < 0) { h->err = "pre-epoch time is not supported"; return GCRA_INTERNAL; }
     if (op == 2) { int rc = ensure_room(h, 1); if (rc) return rc; }
+    // a Store-trait call reads / writes a slot's state: after every batch still in flight on the engine's or a
+    // caller's stream (launch_batch orders itself the same way)
+    for (auto &o : h->scr) if (o.back_recorded) CK(cudaStreamWaitEvent(h->stream, o.ev_back, 0));
     store_op_kernel<<<1, 1, 0, h->stream>>>(h->tab, op, stored_key(key_hash), a, b, ttl, now, h->d_op);
     h->launches++;
     CK(cudaMemcpyAsync(h->h_op, h->d_op, 2 * sizeof(StoreOpResult), cudaMemcpyDeviceToHost, h->stream));
@@ -1142,7 +1201,7 @@ static int policy_before_mutation(gcra_engine *h, int64_t now_ns) {
 
 int32_t gcra_store_get(gcra_engine *h, const void *key, uint64_t len, int64_t now_ns, int64_t *value,
                        uint8_t *found) {
-    int rc = store_op(h, 0, gcra_hash_key(key, len), 0, 0, 0, now_ns);
+    int rc = store_op(h, 0, engine_hash(h, key, len), 0, 0, 0, now_ns);
     if (rc) return rc;
     if (found) *found = (uint8_t)h->h_op[0].flag;
     if (value) *value = h->h_op[0].value;
@@ -1153,7 +1212,7 @@ int32_t gcra_store_cas(gcra_engine *h, const void *key, uint64_t len, int64_t ol
                        uint64_t ttl_ns, int64_t now_ns, uint8_t *swapped) {
     int rc = policy_before_mutation(h, now_ns);
     if (rc) return rc;
-    rc = store_op(h, 1, gcra_hash_key(key, len), old_value, new_value, ttl_ns, now_ns);
+    rc = store_op(h, 1, engine_hash(h, key, len), old_value, new_value, ttl_ns, now_ns);
     if (rc) return rc;
     if (swapped) *swapped = (uint8_t)h->h_op[0].flag;
     return GCRA_OK;
@@ -1163,7 +1222,7 @@ int32_t gcra_store_set_nx(gcra_engine *h, const void *key, uint64_t len, int64_t
                           int64_t now_ns, uint8_t *stored) {
     int rc = policy_before_mutation(h, now_ns);
     if (rc) return rc;
-    rc = store_op(h, 2, gcra_hash_key(key, len), value, 0, ttl_ns, now_ns);
+    rc = store_op(h, 2, engine_hash(h, key, len), value, 0, ttl_ns, now_ns);
     if (rc) return rc;
     if (h->h_op[0].status) { h->err = "table full"; return GCRA_INTERNAL; }
     if (stored) *stored = (uint8_t)h->h_op[0].flag;
@@ -1237,7 +1296,7 @@ int32_t gcra_rate_limit_batch16(gcra_engine *h, uint64_t n, const gcra_request16
 
 int32_t gcra_rate_limit(gcra_engine *h, const void *key, uint64_t len, int64_t max_burst, int64_t count_per_period,
                         int64_t period, int64_t quantity, int64_t now_ns, gcra_result *out) {
-    gcra_request r = {gcra_hash_key(key, len), max_burst, count_per_period, period, quantity, now_ns};
+    gcra_request r = {engine_hash(h, key, len), max_burst, count_per_period, period, quantity, now_ns};
     gcra_result tmp;
     int rc = host_batch(h, 1, &r, sizeof(r), false, 0, &tmp);
     if (rc) { if (out) { memset(out, 0, sizeof(*out)); out->status = GCRA_INTERNAL; } return rc; }
@@ -1339,6 +1398,22 @@ int32_t gcra_ring_poll(gcra_engine *h, uint32_t slot, int32_t *done) {
 // ---- sweep / introspection ---------------------------------------------------------------------
 int32_t gcra_sweep(gcra_engine *h, int64_t now_ns, uint64_t *removed) { return do_sweep(h, now_ns, removed); }
 
+// The store kind's own sweep policy (maybe_clean_expired: adaptive_cleanup.rs:205-211, periodic.rs:128-142,
+// probabilistic.rs:110-125) evaluated against the counters of everything finished so far.  The host-buffer calls
+// and the ring do this themselves before every batch; the device-resident, pipelined and sharded submissions
+// cannot (the requests' clocks live on the device): their caller ticks the policy with its own clock.
+int32_t gcra_policy_tick(gcra_engine *h, int64_t now_ns, uint64_t *swept) {
+    CK(cudaSetDevice(h->device));
+    if (swept) *swept = 0;
+    if (h->kind == GCRA_STORE_MANUAL) return GCRA_OK;
+    for (auto &o : h->scr) if (o.back_recorded) CK(cudaEventSynchronize(o.ev_back));
+    RC(refresh_counters(h, true));
+    const uint64_t before = h->h_counters[C_SWEPT];
+    RC(apply_policy(h, now_ns));
+    if (swept) { RC(refresh_counters(h, true)); *swept = h->h_counters[C_SWEPT] - before; }
+    return GCRA_OK;
+}
+
 uint64_t gcra_len(gcra_engine *h) {
     cudaSetDevice(h->device);
     if (refresh_counters(h, true)) return 0;
@@ -1426,6 +1501,7 @@ struct SnapshotHeader {
     uint32_t version, total_lines, nb_main, stash_slots;
     uint64_t capacity;
     uint64_t counters[C_COUNT];
+    uint64_t hash_seed[2];           // (version 2) the identities in the table were made with this seed
 };
 const char SNAP_MAGIC[8] = {'G', 'C', 'R', 'A', 'B', '2', '0', '0'};
 const size_t SNAP_CHUNK = 32u << 20;
@@ -1456,7 +1532,7 @@ int32_t gcra_snapshot_save(gcra_engine *h, const char *path) {
     if (!f) { h->err = std::string("snapshot: cannot open ") + path; return GCRA_INTERNAL; }
     SnapshotHeader hd{};
     memcpy(hd.magic, SNAP_MAGIC, 8);
-    hd.version = 1; hd.total_lines = h->total_lines; hd.nb_main = h->tab.nb_main; hd.stash_slots = h->tab.stash_slots;
+    hd.version = 2; hd.hash_seed[0] = h->hash_seed[0]; hd.hash_seed[1] = h->hash_seed[1]; hd.total_lines = h->total_lines; hd.nb_main = h->tab.nb_main; hd.stash_slots = h->tab.stash_slots;
     hd.capacity = h->capacity;
     int rc = GCRA_OK;
     if (cudaMemcpy(hd.counters, h->tab.counters, sizeof(hd.counters), cudaMemcpyDeviceToHost) != cudaSuccess ||
@@ -1476,7 +1552,7 @@ int32_t gcra_snapshot_load(gcra_engine *h, const char *path) {
     FILE *f = fopen(path, "rb");
     if (!f) { h->err = std::string("snapshot: cannot open ") + path; return GCRA_INTERNAL; }
     SnapshotHeader hd{};
-    if (fread(&hd, sizeof(hd), 1, f) != 1 || memcmp(hd.magic, SNAP_MAGIC, 8) != 0 || hd.version != 1) {
+    if (fread(&hd, sizeof(hd), 1, f) != 1 || memcmp(hd.magic, SNAP_MAGIC, 8) != 0 || hd.version != 2) {
         fclose(f); h->err = "snapshot: bad header"; return GCRA_INTERNAL;
     }
     int rc = GCRA_OK;
@@ -1503,6 +1579,8 @@ int32_t gcra_snapshot_load(gcra_engine *h, const char *path) {
     fclose(f);
     if (rc) return rc;
     CK(cudaMemcpy(h->tab.counters, hd.counters, sizeof(hd.counters), cudaMemcpyHostToDevice));
+    h->hash_seed[0] = hd.hash_seed[0];
+    h->hash_seed[1] = hd.hash_seed[1];
     h->occupied_ub = hd.counters[C_OCCUPIED];
     h->seen_allowed = hd.counters[C_ALLOWED];
     h->seen_expired_hits = hd.counters[C_EXPIRED_HITS];
@@ -1547,8 +1625,10 @@ int32_t gcra_shard_init(gcra_engine *h, int32_t rank, int32_t world, const void 
     CK(cudaEventCreateWithFlags(&sh->ev_tmp, cudaEventDisableTiming));
     for (auto &sl : sh->slots) {
         CK(cudaMalloc(&sl.routed, (size_t)max_rows * sizeof(gcra_request)));
-        CK(cudaMalloc(&sl.recv_req, (size_t)max_rows * sizeof(gcra_request)));
-        CK(cudaMalloc(&sl.recv_res, (size_t)max_rows * sizeof(gcra_result)));
+        // a shard can receive up to world x max_rows rows in one tick (every rank's whole tick): sized for that, so
+        // no rank ever has to bail out of a tick its peers have already posted their sends for
+        CK(cudaMalloc(&sl.recv_req, (size_t)world * max_rows * sizeof(gcra_request)));
+        CK(cudaMalloc(&sl.recv_res, (size_t)world * max_rows * sizeof(gcra_result)));
         CK(cudaMalloc(&sl.back_res, (size_t)max_rows * sizeof(gcra_result)));
         CK(cudaMalloc(&sl.src_index, (size_t)max_rows * sizeof(u32)));
         CK(cudaMalloc(&sl.counts_dev, 2 * ROUTE_MAX_SHARDS * sizeof(u32)));
@@ -1571,9 +1651,15 @@ static int shard_issue_decide_return(gcra_engine *h) {
     sh->pending = -1;
     const int W = sh->world;
     cudaEvent_t done = nullptr;
-    RC(launch_pipelined(h, sl.n_recv, sl.recv_req, false, 0, sl.recv_res, sl.ev_routed, &done));
-    if (done) CK(cudaStreamWaitEvent(sh->s_return, done, 0));
-    else CK(cudaStreamWaitEvent(sh->s_return, sl.ev_routed, 0));
+    // (more rows than one engine batch carries: several batches, cut anywhere -- the order is kept)
+    for (uint32_t a = 0; a < sl.n_recv || a == 0; a += h->max_batch) {
+        const uint32_t m = std::min<uint32_t>(sl.n_recv - a, h->max_batch);
+        cudaEvent_t dn = nullptr;
+        RC(launch_pipelined(h, m, sl.recv_req + a, false, 0, sl.recv_res + a, sl.ev_routed, &dn));
+        if (dn) { done = dn; CK(cudaStreamWaitEvent(sh->s_return, dn, 0)); }
+        if (sl.n_recv == 0) break;
+    }
+    if (!done) CK(cudaStreamWaitEvent(sh->s_return, sl.ev_routed, 0));
     NK(nccl_rt::g_api.GroupStart());
     for (int p = 0; p < W; p++) {
         // results of the rows peer p sent me go back to p; my own rows' results arrive in partition order
@@ -1637,8 +1723,7 @@ int32_t gcra_shard_submit(gcra_engine *h, uint64_t n64, const gcra_request *d_re
         sl.send_off[p] = so; sl.recv_off[p] = ro;
         so += sl.send[p]; ro += sl.recv[p];
     }
-    if (ro > sh->max_rows) { h->err = "shard received more rows than max_rows"; return GCRA_INTERNAL; }
-    sl.n_recv = (uint32_t)ro;
+    sl.n_recv = (uint32_t)ro;             // <= world x max_rows, which the buffers hold
     NK(nccl_rt::g_api.GroupStart());
     for (int p = 0; p < W; p++) {
         NK(nccl_rt::g_api.Send(sl.routed + sl.send_off[p], sl.send[p] * sizeof(gcra_request), nccl_rt::kUint8, p, sh->comm_req, sh->s_route));
@@ -1707,6 +1792,7 @@ int32_t gcra_p2p_prepare(gcra_engine *h, int32_t rank, int32_t world, uint32_t c
     CK(cudaStreamCreateWithFlags(&p->s_wait, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&p->s_sig, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&p->s_return, cudaStreamNonBlocking));
+    for (auto &e : p->ev_t) CK(cudaEventCreate(&e));
     CK(cudaMalloc(&p->peers_dev, sizeof(P2PPeers)));
     CK(cudaMalloc(&p->tile_counts, (size_t)ROUTE_MAX_SHARDS * ((p->cap + TILE_THREADS - 1) / TILE_THREADS) * sizeof(u32)));
     for (auto &sl : p->slots) {
@@ -1784,6 +1870,7 @@ int32_t gcra_p2p_submit_route(gcra_engine *h, uint64_t n64, const gcra_request *
     }
     // stable partition by owner, rows stored straight into the owners' inboxes, then the flags
     const uint32_t tiles = (n + TILE_THREADS - 1) / TILE_THREADS;
+    if (p->timed) CK(cudaEventRecord(p->ev_t[0], p->s_part));
     if (n) {
         route_count_kernel<<<tiles, TILE_THREADS, 0, p->s_part>>>(d_req, n, W, tiles, p->tile_counts);
         p2p_scan_kernel<<<W, TILE_THREADS, 0, p->s_part>>>(p->tile_counts, tiles, sl.counts_dev);
@@ -1794,6 +1881,7 @@ int32_t gcra_p2p_submit_route(gcra_engine *h, uint64_t n64, const gcra_request *
         CK(cudaMemsetAsync(sl.counts_dev, 0, W * sizeof(u32), p->s_part));
     }
     p2p_signal_req_kernel<<<1, 32, 0, p->s_part>>>(p->peers_dev, sl.counts_dev, W, me, d, tick);
+    if (p->timed) CK(cudaEventRecord(p->ev_t[1], p->s_part));
     h->launches++;
     CK(cudaGetLastError());
     p->routed_pending = true;
@@ -1824,12 +1912,20 @@ int32_t gcra_p2p_submit_finish(gcra_engine *h, gcra_result *d_res) {
     v.nseg = W;
     v.cap_shift = p->cap_shift;
     cudaEvent_t done = nullptr;
-    const uint32_t n_rows = (uint32_t)std::min<uint64_t>((uint64_t)W << p->cap_shift, h->max_batch);
+    // Room in the table for the keys this tick may insert.  How many rows arrive is only known on the device; with a
+    // hash-sharded key space it is about what this rank submitted itself, so 1.25 x that (+ slack) is reserved -- a
+    // reservation of the full inbox would make the host wait for the device every tick.  Should a tick bring more
+    // NEW keys than the table has room for, the surplus rows are answered with GCRA_INTERNAL ("table full"), as
+    // find_or_claim always does; the next tick's check then sees the real occupancy and grows the table.
+    const uint32_t n_rows = (uint32_t)std::min<uint64_t>((uint64_t)sl.n + sl.n / 4 + 4096, std::min<uint64_t>((uint64_t)W << p->cap_shift, h->max_batch));
+    if (p->timed) CK(cudaEventRecord(p->ev_t[2], p->s_wait));
     RC(launch_pipelined_view(h, v, n_rows, false, 0, sl.ev_wait, &done));
     CK(cudaStreamWaitEvent(p->s_sig, done, 0));
+    if (p->timed) CK(cudaEventRecord(p->ev_t[3], p->s_sig));
     p2p_signal_res_kernel<<<1, 32, 0, p->s_sig>>>(p->peers_dev, W, me, tick);
     // sender again: every owner's results of this tick are in my outbox -> input order, into the caller's buffer
     p2p_wait_kernel<<<1, 32, 0, p->s_return>>>(hdr, 1, W, tick);
+    if (p->timed) CK(cudaEventRecord(p->ev_t[4], p->s_return));
     if (sl.n) {
         const uint32_t tiles = (sl.n + TILE_THREADS - 1) / TILE_THREADS;
         p2p_unpermute_kernel<<<tiles, TILE_THREADS, 0, p->s_return>>>((const unsigned char *)p->window + p->outbox_off, sl.res_loc,
@@ -1837,8 +1933,29 @@ int32_t gcra_p2p_submit_finish(gcra_engine *h, gcra_result *d_res) {
         h->launches++;
     }
     CK(cudaEventRecord(sl.ev_done, p->s_return));
+    if (p->timed) { CK(cudaEventRecord(p->ev_t[5], p->s_return)); p->timed_valid = true; }
     h->launches += 3;
     CK(cudaGetLastError());
+    return GCRA_OK;
+}
+
+// stage times (ms) of the most recent tick submitted with timing on (gcra_p2p_set_timing(h, 1)) -- meaningful when
+// ticks are run one at a time (submit, join): [0] partition + transfer + flags, [1] until every sender's rows are
+// here (includes the other ranks' skew), [2] the engine over the inbox, [3] until every owner's results are here,
+// [4] un-permutation
+int32_t gcra_p2p_set_timing(gcra_engine *h, int32_t on) {
+    P2P *p = h->p2p;
+    if (!p) { h->err = "gcra_p2p_prepare first"; return GCRA_INTERNAL; }
+    p->timed = on != 0;
+    return GCRA_OK;
+}
+
+int32_t gcra_p2p_last_tick_ms(gcra_engine *h, float out[5]) {
+    CK(cudaSetDevice(h->device));
+    P2P *p = h->p2p;
+    if (!p || !p->timed_valid) { h->err = "no timed tick yet"; return GCRA_INTERNAL; }
+    CK(cudaEventSynchronize(p->ev_t[5]));
+    for (int i = 0; i < 5; i++) CK(cudaEventElapsedTime(&out[i], p->ev_t[i], p->ev_t[i + 1]));
     return GCRA_OK;
 }
 

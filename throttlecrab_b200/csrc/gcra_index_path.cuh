@@ -280,6 +280,11 @@ decide_index_kernel(Table t, BatchView b, const PolicyDerived *__restrict__ pol,
     constexpr u32 RSZ = COMPACT ? sizeof(gcra_request16) : sizeof(gcra_request);
     __shared__ __align__(128) unsigned char stage[2][TILE_THREADS * RSZ];
     __shared__ __align__(8) u64 bar[2];
+    // results leave through shared memory: a tile's 256 results are written out as 512 consecutive 16-byte pieces
+    // (a warp store covers 512 contiguous bytes).  A segment's result array may be a peer GPU's outbox: a lane
+    // storing the two halves of its own row would put 16-byte packets on NVLink.
+    __shared__ __align__(16) longlong2 rstage[2][TILE_THREADS * 2];
+    __shared__ unsigned char rwrite[2][TILE_THREADS];
     if (threadIdx.x == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
@@ -327,6 +332,7 @@ decide_index_kernel(Table t, BatchView b, const PolicyDerived *__restrict__ pol,
         const u32 slot = slot_c;
         const RunState s = s_c;
         const u32 bits = bits_c;
+        rwrite[buf][threadIdx.x] = 0;
         if (slot != t.null_slot && (bits & F_DEFER)) {
             // the previous batch still works on this key (or on one sharing its entry): not evaluated here, the
             // whole key goes to this batch's sorted tail
@@ -339,7 +345,11 @@ decide_index_kernel(Table t, BatchView b, const PolicyDerived *__restrict__ pol,
             Outputs o;
             if (dbg & 8) { d.allowed = (r.q & 1) != 0; d.live = true; d.new_tat = r.now; d.new_exp = r.now + r.dvt; d.tat = s.tat; d.allow_at = 0; o.remaining = r.q; o.reset_after = r.ei; o.retry_after = 0; }
             else { d = decide(s.tat, s.exp, r); o = outputs_of(d, r); }
-            if (!(dbg & 2)) write_result(b.res_at(row), o.remaining, o.reset_after, o.retry_after, 0, d.allowed ? 1 : 0);
+            if (!(dbg & 2)) {
+                rstage[buf][threadIdx.x * 2] = make_longlong2(o.remaining, o.reset_after);
+                rstage[buf][threadIdx.x * 2 + 1] = make_longlong2(o.retry_after, (i64)(u32)0 | ((i64)(d.allowed ? 1 : 0) << 32));
+                rwrite[buf][threadIdx.x] = 1;
+            }
             const bool mut = d.allowed && ((d.new_tat != s.tat) | (d.new_exp != s.exp));
             // a write over an entry that exists but is expired (adaptive_cleanup.rs:233,267)
             const bool hit = d.allowed && !d.live && s.exp >= 0;
@@ -366,7 +376,17 @@ decide_index_kernel(Table t, BatchView b, const PolicyDerived *__restrict__ pol,
                 }
             }
         }
-        __syncthreads();   // everybody is done with stage[buf]
+        __syncthreads();   // everybody is done with stage[buf]; the tile's results are staged
+        {
+            // rows that failed validation (pass A wrote their error) or were deferred (the tail will write them) keep
+            // their place: only staged rows are stored
+            longlong2 *dst = reinterpret_cast<longlong2 *>(b.res_at(cur.row0));
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const u32 c = threadIdx.x + k * TILE_THREADS;
+                if (rwrite[buf][c >> 1]) dst[c] = rstage[buf][c];
+            }
+        }
         if (!has_nxt) break;
         if (has_nn && threadIdx.x == 0) issue_tile(stage[buf], &bar[buf], nn, RSZ);
         tile += G;

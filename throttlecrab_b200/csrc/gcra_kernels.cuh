@@ -1006,8 +1006,14 @@ constexpr int SWEEP_UNROLL = 4;
 
 // One thread per 32-byte SECTOR of the state array (two slots): two 128-bit loads, and when either entry has
 // expired the whole sector is written back (two 128-bit stores), so DRAM only ever sees full-sector writes.
+// `mode` (tuning, GCRA_SWEEP_MODE): 0 plain stores; 1 streaming stores (st.global.cs: the reset pairs are not read
+// again soon, they need not displace the scan's lines in L2); 2 only the expired 16-byte pair is written.
+__device__ __forceinline__ void st_stream(void *p, longlong2 v) {
+    asm volatile("st.global.cs.v2.s64 [%0], {%1, %2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
+}
+
 __global__ void __launch_bounds__(TILE_THREADS)
-sweep_kernel(Table t, u64 total_slots, i64 now) {
+sweep_kernel(Table t, u64 total_slots, i64 now, int mode) {
     u32 removed = 0;
     const u64 total_pairs = total_slots >> 1;            // the slot count is a power of two >= 64
     const u64 stride = (u64)gridDim.x * TILE_THREADS;
@@ -1028,8 +1034,11 @@ sweep_kernel(Table t, u64 total_slots, i64 now) {
             const bool xa = ea >= 0 && ea <= now, xb = eb >= 0 && eb <= now;   // entries Store::get no longer shows
             if (xa | xb) {
                 longlong2 *dst = reinterpret_cast<longlong2 *>(&t.state[2 * p]);
-                dst[0] = xa ? make_longlong2(0, EXP_EMPTY) : make_longlong2((i64)a[u].x, (i64)a[u].y);
-                dst[1] = xb ? make_longlong2(0, EXP_EMPTY) : make_longlong2((i64)b[u].x, (i64)b[u].y);
+                const longlong2 va = xa ? make_longlong2(0, EXP_EMPTY) : make_longlong2((i64)a[u].x, (i64)a[u].y);
+                const longlong2 vb = xb ? make_longlong2(0, EXP_EMPTY) : make_longlong2((i64)b[u].x, (i64)b[u].y);
+                if (mode == 1) { st_stream(dst, va); st_stream(dst + 1, vb); }
+                else if (mode == 2) { if (xa) dst[0] = va; if (xb) dst[1] = vb; }
+                else { dst[0] = va; dst[1] = vb; }
                 removed += (xa ? 1 : 0) + (xb ? 1 : 0);
             }
         }

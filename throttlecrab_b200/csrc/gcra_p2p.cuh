@@ -70,19 +70,26 @@ p2p_scan_kernel(u32 *__restrict__ tile_counts, u32 num_tiles, u32 *__restrict__ 
 
 // stable partition + transfer: row i goes to position (offset of its tile for its owner + rank among the tile's
 // earlier rows of that owner) of segment (slot, me) in the OWNER's inbox; res_loc[i] remembers where its result
-// will arrive in my outbox
+// will arrive in my outbox.  The tile's rows are first grouped by owner in shared memory, then written out as
+// contiguous 16-byte pieces -- a warp's store covers 512 consecutive bytes of one inbox, which is what NVLink wants
+// (a lane storing the three pieces of its own row would send 16-byte packets).
 __global__ void __launch_bounds__(TILE_THREADS)
 p2p_scatter_kernel(const gcra_request *__restrict__ req, u32 n, u32 world, u32 me, u32 slot, u32 cap_shift,
                    u32 num_tiles, const u32 *__restrict__ tile_offsets, const P2PPeers *__restrict__ peers,
                    u32 *__restrict__ res_loc) {
     constexpr int NW = TILE_THREADS / 32;
     __shared__ u32 wc[NW][ROUTE_MAX_SHARDS];
+    __shared__ u32 lbase[ROUTE_MAX_SHARDS + 1];              // first tile-local position of every owner's rows
+    __shared__ unsigned long long dst_base[ROUTE_MAX_SHARDS]; // where the tile's rows of owner o start in o's inbox
+    __shared__ __align__(16) ulonglong2 rows[TILE_THREADS * 3];
+    __shared__ unsigned char own_of[TILE_THREADS];           // owner of the row at a tile-local position
     const u32 w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x < NW * ROUTE_MAX_SHARDS) (&wc[0][0])[threadIdx.x] = 0;
     __syncthreads();
     const u32 i = blockIdx.x * TILE_THREADS + threadIdx.x;
+    const u32 cnt = min((u32)TILE_THREADS, n - blockIdx.x * TILE_THREADS);
     const bool valid = i < n;
-    ulonglong2 r0, r1, r2;
+    ulonglong2 r0 = make_ulonglong2(0, 0), r1 = r0, r2 = r0;
     u32 own = 0;
     if (valid) {
         const ulonglong2 *s = reinterpret_cast<const ulonglong2 *>(req + i);
@@ -96,15 +103,33 @@ p2p_scatter_kernel(const gcra_request *__restrict__ req, u32 n, u32 world, u32 m
     if (threadIdx.x < world) {
         u32 acc = 0;
         for (int x = 0; x < NW; x++) { u32 v = wc[x][threadIdx.x]; wc[x][threadIdx.x] = acc; acc += v; }
+        lbase[threadIdx.x + 1] = acc;                        // the owner's count in this tile (scanned below)
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 acc = 0;
+        lbase[0] = 0;
+        for (u32 o = 0; o < world; o++) { const u32 c = lbase[o + 1]; lbase[o + 1] = acc + c; acc += c; }
+    }
+    if (threadIdx.x < world) {
+        const u32 o = threadIdx.x;
+        const size_t seg = ((size_t)slot * world + me) << cap_shift;
+        const unsigned char *base = (const unsigned char *)__ldg((const u64 *)&peers->inbox[o]);
+        dst_base[o] = (unsigned long long)(base + (seg + tile_offsets[o * num_tiles + blockIdx.x]) * sizeof(gcra_request));
     }
     __syncthreads();
     if (valid) {
-        const u32 pos = tile_offsets[own * num_tiles + blockIdx.x] + wc[w][own] + rank;
-        const size_t seg = ((size_t)slot * world + me) << cap_shift;
-        unsigned char *base = (unsigned char *)__ldg((const u64 *)&peers->inbox[own]);
-        ulonglong2 *d = reinterpret_cast<ulonglong2 *>(base + (seg + pos) * sizeof(gcra_request));
-        d[0] = r0; d[1] = r1; d[2] = r2;                       // NVLink store (local when own == me)
-        res_loc[i] = (own << cap_shift) | pos;
+        const u32 in_owner = wc[w][own] + rank;              // rank among the tile's rows of this owner
+        const u32 lpos = lbase[own] + in_owner;
+        rows[lpos * 3] = r0; rows[lpos * 3 + 1] = r1; rows[lpos * 3 + 2] = r2;
+        own_of[lpos] = (unsigned char)own;
+        res_loc[i] = (own << cap_shift) | (tile_offsets[own * num_tiles + blockIdx.x] + in_owner);
+    }
+    __syncthreads();
+    for (u32 c = threadIdx.x; c < cnt * 3; c += TILE_THREADS) {
+        const u32 lpos = c / 3, o = own_of[lpos];
+        ulonglong2 *d = reinterpret_cast<ulonglong2 *>(dst_base[o]) + (c - lbase[o] * 3);
+        *d = rows[c];                                        // NVLink store (local when o == me)
     }
 }
 

@@ -50,11 +50,12 @@ class CudaOps:
 
 
 class _Slot:
-    def __init__(self, max_rows, device):
+    def __init__(self, max_rows, device, world=1):
         u8 = dict(dtype=torch.uint8, device=device)
         self.routed = torch.empty(max_rows * REQ_B, **u8)
-        self.recv_req = torch.empty(max_rows * REQ_B, **u8)
-        self.recv_res = torch.empty(max_rows * RES_B, **u8)
+        # a shard can receive every rank's whole tick: sized for that, no rank ever bails out of a tick alone
+        self.recv_req = torch.empty(world * max_rows * REQ_B, **u8)
+        self.recv_res = torch.empty(world * max_rows * RES_B, **u8)
         self.back_res = torch.empty(max_rows * RES_B, **u8)
         self.src_index = torch.empty(max_rows, dtype=torch.int32, device=device)
         self.counts = torch.zeros(16, dtype=torch.int32, device=device)
@@ -72,7 +73,7 @@ class ShardedLimiter:
         self.ops = ops if ops is not None else CudaOps(limiter)
         self.max_rows = max_rows or limiter.store.max_batch
         self.cuda = device.type == "cuda"
-        self.slots = [_Slot(self.max_rows, device) for _ in range(DEPTH if self.cuda else 1)]
+        self.slots = [_Slot(self.max_rows, device, self.world) for _ in range(DEPTH if self.cuda else 1)]
         self.n_submitted = 0
         self.pending = None
         self.returned = []
@@ -107,16 +108,17 @@ class ShardedLimiter:
         else:
             both = slot.both.tolist()
         send_l, recv_l = both[:W], both[W:]
-        n_recv = sum(recv_l)
-        if n_recv > self.max_rows:
-            raise RuntimeError("shard received %d rows > max_batch %d" % (n_recv, self.max_rows))
+        n_recv = sum(recv_l)          # <= world * max_rows, which the buffers hold
         self.dist.all_to_all_single(slot.recv_req[:n_recv * REQ_B], slot.routed[:n * REQ_B],
                                     output_split_sizes=[c * REQ_B for c in recv_l],
                                     input_split_sizes=[c * REQ_B for c in send_l], group=self.pg_req)
         return send_l, recv_l, n_recv
 
     def _decide(self, slot, n_recv, stream):
-        self.ops.decide(n_recv, slot.recv_req, slot.recv_res, stream)
+        # more rows than one engine batch carries: several batches, cut anywhere (the order is kept)
+        for a in range(0, max(n_recv, 1), self.max_rows):
+            m = min(n_recv - a, self.max_rows)
+            self.ops.decide(m, slot.recv_req[a * REQ_B:], slot.recv_res[a * RES_B:], stream)
 
     def _return(self, slot, d_res, n, send_l, recv_l, n_recv, stream):
         self.dist.all_to_all_single(slot.back_res[:n * RES_B], slot.recv_res[:n_recv * RES_B],
