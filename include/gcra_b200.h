@@ -297,6 +297,19 @@ int32_t gcra_actor_throttle(gcra_actor *a, const void *key, uint64_t len, int64_
 int32_t gcra_actor_stats(gcra_actor *a, uint64_t out[3]);
 void gcra_actor_destroy(gcra_actor *a);
 
+/* ---- batch RESP ingest: a pipelined read buffer -> request rows, results -> reply bytes -------------------------
+ * replaces the per-value parse + per-command await of the Redis transport (transport/redis/resp.rs:28-177,
+ * redis/mod.rs:128-149,221-295) for its hot command.  gcra_resp_parse_throttle walks `buf` once and writes one
+ * request row per plain `THROTTLE key max_burst count_per_period period [quantity]` frame into req_out (e.g. a
+ * pinned ring slot); it never consumes part of a frame.  *stop: 0 buffer ended on a frame boundary, 1 an incomplete
+ * frame follows, 2 a frame follows that is not a plain THROTTLE (hand THAT frame to a general RESP parser, then call
+ * again), 3 max_frames reached.  h (may be NULL) supplies the engine's key-hash seed. */
+int32_t gcra_resp_parse_throttle(gcra_engine *h, const void *buf, uint64_t len, int64_t now_ns, uint32_t max_frames,
+                                 gcra_request *req_out, uint64_t *consumed, uint32_t *n_frames, int32_t *stop);
+/* replies of n decided THROTTLE commands, in order (mod.rs:274-285, seconds as types.rs:87-97); needs cap >= 160 n */
+uint64_t gcra_resp_format_replies(const gcra_request *req, const gcra_result *res, uint32_t n, void *out,
+                                  uint64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

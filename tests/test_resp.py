@@ -108,7 +108,7 @@ class OracleEngine:
 
 
 def _replies(buf, engine=None):
-    out, consumed, _ = process_pipeline(buf, engine or OracleEngine(), NOW)
+    out, consumed, _, _ = process_pipeline(buf, engine or OracleEngine(), NOW)
     p, vals, pos = RespParser(), [], 0
     while pos < len(out):
         v, c = p.parse(out[pos:])
@@ -121,10 +121,10 @@ def test_commands_known_answers():
     buf = (_cmd("PING") + _cmd("PING", "hello") + _throttle("test_key", 10, 100, 60)       # redis_test.rs:99-130
            + _throttle("test_key2", 10, 100, 60, 5) + _cmd("UNKNOWN") + _cmd("THROTTLE", "test_key")
            + _cmd("THROTTLE", "test_key", "not_a_number", "100", "60") + _cmd("THROTTLE", "test_key", "-5", "100", "60")
-           + _cmd("THROTTLE", None, "10", "100", "60") + _throttle("", 10, 100, 60) + _cmd("QUIT")
+           + _cmd("THROTTLE", None, "10", "100", "60") + _throttle("", 10, 100, 60)
            + _throttle("large_quantity_key", 10, 100, 60, 15) + _throttle("zero_quantity_key", 10, 100, 60, 0)
            + _cmd("THROTTLE", "ik", 10, 100, 60) + _cmd("throttle", "ik", "10", "100", "60")
-           + _cmd("THROTTLE", "neg", "10", "100", "60", "-1"))
+           + _cmd("THROTTLE", "neg", "10", "100", "60", "-1") + _cmd("QUIT"))
     v, consumed = _replies(buf)
     assert consumed == len(buf)
     assert v[0] == SimpleString("PONG") and v[1] == BulkString("hello")
@@ -136,11 +136,11 @@ def test_commands_known_answers():
     assert v[7][0] == "error" and v[7][1].startswith("ERR")                                    # :486-489 (InvalidRateLimit)
     assert "invalid key" in v[8][1]                                                            # :658-676
     assert v[9][1][:3] == [Integer(1), Integer(10), Integer(9)]                                # :633-656 empty key
-    assert v[10] == SimpleString("OK")
-    assert v[11][1][0] == Integer(0) and v[11][1][2] == Integer(10)                            # :384-395
-    assert v[12][1][0] == Integer(1) and v[12][1][2] == Integer(10)                            # :491-502
-    assert v[13][1][2] == Integer(9) and v[14][1][2] == Integer(8)                             # integer args, lower case
-    assert v[15] == Error("ERR Rate limit check failed: negative quantity: -1")
+    assert v[10][1][0] == Integer(0) and v[10][1][2] == Integer(10)                            # :384-395
+    assert v[11][1][0] == Integer(1) and v[11][1][2] == Integer(10)                            # :491-502
+    assert v[12][1][2] == Integer(9) and v[13][1][2] == Integer(8)                             # integer args, lower case
+    assert v[14] == Error("ERR Rate limit check failed: negative quantity: -1")
+    assert v[15] == SimpleString("OK")                                                         # QUIT, last
 
 
 def test_pipeline_keeps_arrival_order_and_partial_tail():
@@ -170,3 +170,113 @@ def test_pipeline_against_the_engine():
     assert [v[i][1][2] for i in (1, 3, 4)] == [Integer(9), Integer(8), Integer(7)]
     assert v[5][1][:2] == [Integer(1), Integer(2**63 - 1)]                                     # :677-697
     assert v[6][1][:3] == [Integer(1), Integer(1), Integer(0)]                                 # :699-716
+
+
+def test_pipeline_error_and_quit_like_the_connection_loop():
+    """redis/mod.rs:128-149: commands before a protocol error are applied and answered, then the connection closes;
+    nothing after QUIT is executed."""
+    one = _throttle("order_key", 2, 100, 60)
+    eng = OracleEngine()
+    out, consumed, n, close = process_pipeline(one + one + b"?garbage\r\n" + one, eng, NOW)
+    assert close == "error" and n == 2 and consumed == 2 * len(one)
+    vals, pos, p = [], 0, RespParser()
+    while pos < len(out):
+        v, c = p.parse(out[pos:])
+        vals.append(v)
+        pos += c
+    assert [x[1][0] for x in vals] == [Integer(1), Integer(1)]
+    out, consumed, n, close = process_pipeline(one + _cmd("QUIT") + one, eng, NOW)
+    assert close == "quit" and n == 1 and consumed == len(one) + len(_cmd("QUIT"))
+    assert out.endswith(b"+OK\r\n")
+    v0, _ = RespParser().parse(out)
+    assert v0[1][0] == Integer(0)                      # the key was exhausted by the two requests above; the third
+    # command (after QUIT) was never applied: a fresh engine would have allowed it
+
+
+class _FakeStore:
+    """tests only (no GPU): what process_pipeline_native needs from a limiter besides the two C helpers"""
+
+    def __init__(self):
+        self.eng = OracleEngine()
+
+    def _check(self, rc):
+        assert rc == 0
+
+    def hash_seed(self):
+        return (0, 0)
+
+
+class _FakeLimiter:
+    def __init__(self):
+        from throttlecrab_b200 import _native
+        self._L, self._h, self.store = _native.lib(), None, _FakeStore()
+
+    def rate_limit_batch(self, req):
+        return self.store.eng(req)
+
+
+def test_native_batch_parser_matches_the_general_parser():
+    """gcra_resp_parse_throttle + gcra_resp_format_replies (csrc/gcra_resp.inc) against the mirror of resp.rs on a
+    pipeline that mixes plain THROTTLE frames with everything the fast path must hand back: other commands, RESP
+    integer arguments, lower case, quantity, negative numbers, non-numeric arguments, a split tail."""
+    from throttlecrab_b200.resp import process_pipeline_native
+    frames = [_throttle("k%d" % (i % 7), 3, 100, 60) for i in range(50)]
+    frames[5] = _cmd("PING")
+    frames[9] = _cmd("throttle", "k1", 3, 100, 60)                     # RESP integers: general parser
+    frames[12] = _throttle("k2", 3, 100, 60, 2)
+    frames[13] = _throttle("k2", 3, 100, 60, -1)                       # negative quantity -> error reply
+    frames[20] = _cmd("THROTTLE", "k3", "abc", "100", "60")            # not a number -> ERR invalid max_burst
+    frames[21] = _cmd("tHrOtTlE", "k3", "3", "100", "60")
+    frames[30] = _cmd("THROTTLE", "k4", "0", "100", "60")              # invalid rate limit (engine error)
+    frames[31] = _cmd("UNKNOWN")
+    frames[40] = _throttle("binary\r\nkey", 3, 100, 60)                # CRLF inside a bulk string
+    buf = b"".join(frames) + _throttle("tail", 3, 100, 60)[:-5]
+    want = process_pipeline(buf, OracleEngine(), NOW)
+    got = process_pipeline_native(buf, _FakeLimiter(), NOW)
+    assert got == want
+    assert got[1] == len(b"".join(frames)) and got[2] == 47 and got[3] is None
+    # errors and QUIT exactly as the general pipeline
+    bad = frames[0] + b"!x\r\n" + frames[1]
+    assert process_pipeline_native(bad, _FakeLimiter(), NOW) == process_pipeline(bad, OracleEngine(), NOW)
+    q = frames[0] + _cmd("quit") + frames[1]
+    assert process_pipeline_native(q, _FakeLimiter(), NOW) == process_pipeline(q, OracleEngine(), NOW)
+
+
+def test_native_batch_parser_limits():
+    """frames the fast path must not swallow: huge declared lengths, 20-digit numbers, wrong arity"""
+    import ctypes as C
+    from throttlecrab_b200 import _native
+    L = _native.lib()
+    req = np.zeros(8, tc.REQ_DTYPE)
+
+    def run(buf):
+        used, cnt, stop = C.c_uint64(), C.c_uint32(), C.c_int32()
+        assert L.gcra_resp_parse_throttle(None, buf, len(buf), NOW, 8, req.ctypes.data, C.byref(used), C.byref(cnt),
+                                          C.byref(stop)) == 0
+        return used.value, cnt.value, stop.value
+    ok = _throttle("k", 5, 10, 60)
+    assert run(ok) == (len(ok), 1, 0)
+    assert int(req[0]["key_hash"]) == tc.hash_key("k") and int(req[0]["quantity"]) == 1 and int(req[0]["now_ns"]) == NOW
+    assert run(ok + ok[:10]) == (len(ok), 1, 1)                                        # incomplete frame: read more
+    assert run(_cmd("THROTTLE", "k", "99999999999999999999", "10", "60"))[1:] == (0, 2)   # 20 digits: general parser
+    assert run(b"*5\r\n$8\r\nTHROTTLE\r\n$999999999999\r\n")[1:] == (0, 2)              # over MAX_BULK_STRING_SIZE
+    assert run(_cmd("THROTTLE", "k", "5", "10"))[1:] == (0, 2)                           # wrong arity
+    assert run(_throttle("k", 9223372036854775807, 1, 1))[1:] == (1, 0)                # i64::MAX fits
+    assert run(ok * 9)[1:] == (8, 3)                                                   # max_frames
+
+
+@pytest.mark.gpu
+def test_native_pipeline_through_the_pinned_ring():
+    """A pipelined read buffer -> request rows written straight into a pinned ring slot -> one engine batch -> reply
+    bytes; equal to the general pipeline over the blocking API on a twin engine."""
+    from throttlecrab_b200.resp import process_pipeline_native
+    frames = [_throttle("user:%d" % (i % 97), 5, 10, 60) for i in range(3000)]
+    frames[100] = _cmd("PING")
+    frames[2000] = _cmd("throttle", "user:1", 5, 10, 60)
+    buf = b"".join(frames)
+    a = tc.RateLimiter(tc.PeriodicStore(capacity=1000, created_ns=NOW, max_batch=4096))
+    b = tc.RateLimiter(tc.PeriodicStore(capacity=1000, created_ns=NOW, max_batch=4096))
+    ring = tc.Ring(b, slots=2, slot_capacity=4096)
+    want = process_pipeline(buf, a.rate_limit_batch, NOW)
+    got = process_pipeline_native(buf, b, NOW, ring=ring, slot=1)
+    assert got == want and got[2] == 2999

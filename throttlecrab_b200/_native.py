@@ -127,6 +127,8 @@ SYMBOLS = {
     "gcra_actor_throttle": (_i32, [_vp, C.c_char_p, _u64, _i64, _i64, _i64, _i64, _i64, _vp]),
     "gcra_actor_stats": (_i32, [_vp, C.POINTER(_u64 * 3)]),
     "gcra_actor_destroy": (None, [_vp]),
+    "gcra_resp_parse_throttle": (_i32, [_vp, C.c_char_p, _u64, _i64, _u32, _vp, _pu64, C.POINTER(_u32), C.POINTER(_i32)]),
+    "gcra_resp_format_replies": (_u64, [_vp, _vp, _u32, _vp, _u64]),
     "gcra_owner_of": (_u32, [_u64, _u32]),
     "gcra_route_partition": (_i32, [_vp, _u64, _vp, _u32, _vp, _vp, _vp, _vp]),
     "gcra_route_unpermute": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp]),

@@ -2029,3 +2029,4 @@ int32_t gcra_route_unpermute(gcra_engine *h, uint64_t n, const gcra_result *d_re
 }  // extern "C"
 
 #include "gcra_actor.inc"
+#include "gcra_resp.inc"

@@ -143,7 +143,11 @@ __device__ __forceinline__ Decision decide(i64 s_tat, i64 s_exp, const Req &r) {
     Decision d;
     d.live = s_exp > r.now;
     i64 inc;
+#ifdef GCRA_NO_FASTPATH
+    if (false) {
+#else
     if (ordinary_request(r, &inc) && (!d.live || (s_tat > -(1LL << 61) && s_tat < (1LL << 61)))) {
+#endif
         // fast path: the same sequence (rate_limiter.rs:158-183) in plain 64-bit arithmetic
         d.tat = d.live ? max(s_tat, r.now - r.dvt) : r.now - r.ei;
         d.new_tat = d.tat + inc;
@@ -171,7 +175,11 @@ __device__ __forceinline__ Outputs outputs_of(const Decision &d, const Req &r) {
     Outputs o;
     i64 cur = d.allowed ? d.new_tat : d.tat;
     // ordinary magnitudes (see ordinary_request; cur is then within +-2^62): nothing below saturates
+#ifdef GCRA_NO_FASTPATH
+    const bool plain = false;
+#else
     const bool plain = ((((u64)r.now >> 61) | ((u64)r.dvt >> 60)) == 0) && cur > -(1LL << 62) && cur < (1LL << 62);
+#endif
     i64 room = plain ? (r.now + r.dvt) - cur : sat_sub(wrap_add(r.now, r.dvt), cur);
     // remaining = max(room / ei, 0) for ei > 0 (truncating).  room <= 0 gives 0.  Both operands below 2^53
     // (always, away from saturation corners): one IEEE double division, exact after a +-1 correction;

@@ -689,7 +689,10 @@ __device__ __forceinline__ void decide_chunk(const Table &t, const u64 *sorted, 
     }
 }
 
-__global__ void __launch_bounds__(DECIDE_THREADS, 1024 / DECIDE_THREADS)
+#ifndef GCRA_DECIDE_MINBLOCKS
+#define GCRA_DECIDE_MINBLOCKS (1024 / GCRA_DECIDE_THREADS)
+#endif
+__global__ void __launch_bounds__(DECIDE_THREADS, GCRA_DECIDE_MINBLOCKS)
 decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ drec, u32 n_host,
               const u32 *__restrict__ n_dev, OutMap out, LongRun *__restrict__ long_runs,
               LongRun *__restrict__ giant_runs, u32 *__restrict__ long_count, int mode) {

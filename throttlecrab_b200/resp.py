@@ -207,20 +207,51 @@ def _plan_command(value):
     return ("throttle", args[1][1], nums[0], nums[1], nums[2], nums[3])
 
 
+def _is_quit(value):
+    """redis/mod.rs:132-135: an array whose first element is the bulk string QUIT (any case)"""
+    return (value[0] == "array" and len(value[1]) > 0 and value[1][0][0] == "bulk"
+            and value[1][0][1] is not None and value[1][0][1].upper() == "QUIT")
+
+
+def _throttle_reply(o, limit, quantity):
+    st = int(o["status"])
+    if st == OK:                                                                 # mod.rs:274-283, types.rs:87-97
+        return Array([Integer(1 if o["allowed"] else 0), Integer(limit), Integer(int(o["remaining"])),
+                      Integer(int(o["reset_after_ns"]) // NS), Integer(int(o["retry_after_ns"]) // NS)])
+    # "ERR {e}" (mod.rs:285) where e = "Rate limit check failed: {CellError}" (actor.rs:252, core/mod.rs:58-65)
+    if st == NEGATIVE_QUANTITY:
+        return Error("ERR Rate limit check failed: negative quantity: %d" % quantity)
+    if st == INVALID_RATE_LIMIT:
+        return Error("ERR Rate limit check failed: invalid rate limit parameters")
+    return Error("ERR Rate limit check failed: internal error")
+
+
 def process_pipeline(buffer, rate_limit_batch, now_ns):
     """Parse every complete command in `buffer`, decide all THROTTLE commands in ONE engine batch
     (`rate_limit_batch(REQ_DTYPE array) -> RES_DTYPE array`, e.g. RateLimiter.rate_limit_batch), and return
-    (reply_bytes, bytes_consumed, n_throttle).  `now_ns` may be an int (one timestamp for the whole buffer,
-    like SystemTime::now() per command at mod.rs:270 read once) or a callable returning one per command."""
+    (reply_bytes, bytes_consumed, n_throttle, close).  `now_ns` may be an int (one timestamp for the whole buffer,
+    like SystemTime::now() per command at mod.rs:270 read once) or a callable returning one per command.
+
+    As in the reference's connection loop (redis/mod.rs:128-149): commands are answered in order; a protocol error
+    on a LATER frame does not undo the commands before it -- they are applied and answered, then `close` is "error"
+    (the reference returns the parser's error, which closes the connection); nothing after a QUIT is executed and
+    `close` is "quit".  Otherwise `close` is None."""
     parser = RespParser()
     data = bytes(buffer)
-    plans, consumed = [], 0
+    plans, consumed, close = [], 0, None
     while consumed < len(data):
-        r = parser.parse(data[consumed:])
+        try:
+            r = parser.parse(data[consumed:])
+        except RespError:
+            close = "error"
+            break
         if r is None:
             break
         plans.append(_plan_command(r[0]))
         consumed += r[1]
+        if _is_quit(r[0]):
+            close = "quit"
+            break
     rows = [p for p in plans if p[0] == "throttle"]
     res = None
     if rows:
@@ -233,18 +264,80 @@ def process_pipeline(buffer, rate_limit_batch, now_ns):
         if p[0] == "reply":
             out.append(RespSerializer.serialize(p[1]))
             continue
-        o, limit = res[j], p[2]
+        out.append(RespSerializer.serialize(_throttle_reply(res[j], p[2], p[5])))
         j += 1
-        st = int(o["status"])
-        if st == OK:                                                             # mod.rs:274-283, types.rs:87-97
-            v = Array([Integer(1 if o["allowed"] else 0), Integer(limit), Integer(int(o["remaining"])),
-                       Integer(int(o["reset_after_ns"]) // NS), Integer(int(o["retry_after_ns"]) // NS)])
-        # "ERR {e}" (mod.rs:285) where e = "Rate limit check failed: {CellError}" (actor.rs:252, core/mod.rs:58-65)
-        elif st == NEGATIVE_QUANTITY:
-            v = Error("ERR Rate limit check failed: negative quantity: %d" % p[5])
-        elif st == INVALID_RATE_LIMIT:
-            v = Error("ERR Rate limit check failed: invalid rate limit parameters")
+    return b"".join(out), consumed, len(rows), close
+
+
+def process_pipeline_native(buffer, limiter, now_ns, ring=None, slot=0):
+    """The same contract as process_pipeline, with the hot command on the native path: gcra_resp_parse_throttle
+    (csrc/gcra_resp.inc) walks the buffer once and writes one request row per plain THROTTLE frame straight into the
+    request array -- the pinned ring slot `ring.req[slot]` when a Ring is given -- and gcra_resp_format_replies
+    writes the replies; only frames that are not plain THROTTLE commands (PING, QUIT, RESP-integer arguments, ...)
+    go through the general parser above.  All THROTTLE commands of the buffer are ONE engine batch (the ring's
+    submit / wait when a ring is given, else rate_limit_batch); replies come back in command order.
+    Returns (reply_bytes, bytes_consumed, n_throttle, close)."""
+    import ctypes as C
+    from . import RES_DTYPE
+    L, h = limiter._L, limiter._h
+    data = bytes(buffer)
+    cap = ring.cap if ring is not None else max(len(data) // 32 + 1, 16)
+    req = ring.req[slot] if ring is not None else np.empty(cap, REQ_DTYPE)
+    parser = RespParser()
+    segs, n, consumed, close = [], 0, 0, None            # segs: ("rows", first, count) | ("reply", value) | ("row", index, limit, qty)
+    now = int(now_ns() if callable(now_ns) else now_ns)
+    while consumed < len(data) and n < cap:
+        used, cnt, stop = C.c_uint64(), C.c_uint32(), C.c_int32()
+        view = data[consumed:]
+        limiter.store._check(L.gcra_resp_parse_throttle(h, view, len(view), now, cap - n,
+                                                        req.ctypes.data + n * REQ_DTYPE.itemsize,
+                                                        C.byref(used), C.byref(cnt), C.byref(stop)))
+        if cnt.value:
+            segs.append(("rows", n, cnt.value))
+            n += cnt.value
+            consumed += used.value
+        if stop.value != 2:
+            break                                         # end of buffer, incomplete frame, or the slot is full
+        try:                                              # one frame for the general parser
+            r = parser.parse(data[consumed:])
+        except RespError:
+            close = "error"
+            break
+        if r is None:
+            break
+        consumed += r[1]
+        plan = _plan_command(r[0])
+        if plan[0] == "throttle":
+            if n >= cap:
+                consumed -= r[1]
+                break
+            req[n] = (hash_key(plan[1]) if not any(limiter.store.hash_seed()) else limiter.store.hash_key(plan[1]),
+                      plan[2], plan[3], plan[4], plan[5], now)
+            segs.append(("row", n, plan[2], plan[5]))
+            n += 1
         else:
-            v = Error("ERR Rate limit check failed: internal error")
-        out.append(RespSerializer.serialize(v))
-    return b"".join(out), consumed, len(rows)
+            segs.append(("reply", plan[1]))
+        if _is_quit(r[0]):
+            close = "quit"
+            break
+    res = None
+    if n:
+        if ring is not None:
+            ring.submit(slot, n, now)
+            ring.wait(slot)
+            res = ring.res[slot]
+        else:
+            res = limiter.rate_limit_batch(req[:n])
+    out = []
+    scratch = C.create_string_buffer(max(n, 1) * 160)
+    for sg in segs:
+        if sg[0] == "reply":
+            out.append(RespSerializer.serialize(sg[1]))
+        elif sg[0] == "row":
+            out.append(RespSerializer.serialize(_throttle_reply(res[sg[1]], sg[2], sg[3])))
+        else:
+            first, cnt = sg[1], sg[2]
+            w = L.gcra_resp_format_replies(req.ctypes.data + first * REQ_DTYPE.itemsize,
+                                           res.ctypes.data + first * RES_DTYPE.itemsize, cnt, scratch, len(scratch))
+            out.append(scratch.raw[:w])
+    return b"".join(out), consumed, n, close
