@@ -202,6 +202,14 @@ int32_t gcra_policy_tick(gcra_engine *h, int64_t now_ns, uint64_t *swept);
 /* len() (periodic.rs:113-116) */
 uint64_t gcra_len(gcra_engine *h);
 int32_t gcra_get_stats(gcra_engine *h, gcra_stats *out);
+/* metrics bridge (throttlecrab-server/src/metrics.rs:24-64,162-173: top denied keys).  After gcra_track_denied(h,
+ * max_keys > 0) a pass over every finished single-GPU batch counts its denied requests per key hash in a device
+ * table; gcra_top_denied returns the k most denied (hash, count) pairs, most denied first, and prunes the table to
+ * its max_keys top entries once more than 3 x max_keys keys have accumulated (the reference's cleanup rule).  Keys
+ * are hashes here -- the caller of the batch entry points owns the strings.  max_keys = 0 switches tracking off. */
+int32_t gcra_track_denied(gcra_engine *h, uint32_t max_keys);
+int32_t gcra_top_denied(gcra_engine *h, uint32_t k, uint64_t *key_hashes, uint64_t *counts, uint32_t *n_out,
+                        uint64_t *dropped);
 /* table entry of a key after the fact: returns found, tat and expiry (saturated to INT64_MAX) */
 int32_t gcra_peek(gcra_engine *h, uint64_t key_hash, int64_t *tat, int64_t *expiry_ns, uint8_t *found);
 /* dump the table to a file / load it back (the reference keeps its state in memory only and loses it on

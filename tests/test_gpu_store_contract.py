@@ -78,3 +78,28 @@ def test_seeded_key_identity(k1_path, tmp_path):
     assert rnd.hash_seed() != (0, 0)
     for s in (st, st2, rnd):
         s.close()
+
+
+def test_top_denied_keys_from_kernel_outputs():
+    """metrics.rs:162-173 (top denied keys), fed from the batches' own request / result rows on the device: equal to a
+    host-side count of the denied rows per key hash."""
+    import numpy as np
+    import traces
+    from gpu_util import engine_requests
+    n_keys = 5000
+    req = traces.config4(n_keys=n_keys, n_ticks=4, tick_size=1 << 15, hot=50)
+    ereq = engine_requests(req)
+    st = tc.ManualStore(capacity=n_keys, created_ns=traces.T0, max_batch=1 << 15)
+    st.track_denied(20000)                                   # room for every key: exact counts
+    lim = tc.RateLimiter(st)
+    res = np.empty(len(req), tc.RES_DTYPE)
+    for a in range(0, len(req), 1 << 15):
+        lim.rate_limit_batch(ereq[a:a + (1 << 15)], out=res[a:a + (1 << 15)])
+    denied = (res["status"] == 0) & (res["allowed"] == 0)
+    keys, cnt = np.unique(ereq["key_hash"][denied], return_counts=True)
+    order = np.lexsort((keys, -cnt))
+    want = [(int(keys[i]), int(cnt[i])) for i in order[:25]]
+    got, dropped = st.top_denied(25)
+    assert dropped == 0 and got == want and want[0][1] > 100
+    assert sum(c for _, c in st.top_denied(20000)[0]) == int(denied.sum())
+    st.close()

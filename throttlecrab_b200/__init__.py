@@ -222,6 +222,17 @@ class _GpuStore:
         self._check(self._L.gcra_sweep(self._h, _ns(now), C.byref(r)))
         return r.value
 
+    def track_denied(self, max_keys):
+        """metrics.rs:162-173: count denied requests per key hash from every finished batch (0 = off)"""
+        self._check(self._L.gcra_track_denied(self._h, max_keys))
+
+    def top_denied(self, k):
+        """[(key_hash, denied_count)] most denied first, and the number of denials dropped by a full table"""
+        keys, cnts = np.zeros(k, np.uint64), np.zeros(k, np.uint64)
+        n, dropped = C.c_uint32(), C.c_uint64()
+        self._check(self._L.gcra_top_denied(self._h, k, keys.ctypes.data, cnts.ctypes.data, C.byref(n), C.byref(dropped)))
+        return [(int(keys[i]), int(cnts[i])) for i in range(n.value)], int(dropped.value)
+
     def policy_tick(self, now):
         """The store kind's sweep policy against the caller's clock (for device-resident / pipelined / sharded
         submissions, which never sweep by themselves); returns the number of entries removed."""

@@ -99,6 +99,8 @@ SYMBOLS = {
     "gcra_policy_tick": (_i32, [_vp, _i64, _pu64]),
     "gcra_len": (_u64, [_vp]),
     "gcra_get_stats": (_i32, [_vp, C.POINTER(Stats)]),
+    "gcra_track_denied": (_i32, [_vp, _u32]),
+    "gcra_top_denied": (_i32, [_vp, _u32, _vp, _vp, C.POINTER(_u32), _pu64]),
     "gcra_peek": (_i32, [_vp, _u64, _pi64, _pi64, _pu8]),
     "gcra_snapshot_save": (_i32, [_vp, C.c_char_p]),
     "gcra_snapshot_load": (_i32, [_vp, C.c_char_p]),

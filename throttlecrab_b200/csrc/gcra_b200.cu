@@ -244,6 +244,9 @@ struct gcra_engine {
     std::vector<RingSlot> ring;
     uint32_t ring_cap = 0;
     bool ring_compact = false;
+    // denied requests per key (gcra_track_denied): device table, updated by a pass over every finished batch
+    DeniedTable denied{};
+    uint32_t denied_max = 0, denied_cap = 0;
     uint64_t hash_seed[2] = {0, 0};  // SipHash key of the string-keyed entry points ((0,0): the unkeyed gcra_hash_key)
     std::string err;
 };
@@ -615,6 +618,17 @@ static int alloc_index_scratch(gcra_engine *h, Scratch &sc, uint32_t rows) {
     return GCRA_OK;
 }
 
+// metrics bridge: count this batch's denied rows per key (single-segment batches: request and result rows local)
+static int enqueue_denied(gcra_engine *h, const BatchView &v, bool compact, cudaStream_t st) {
+    if (!h->denied_max || v.nseg != 1 || v.n == 0) return GCRA_OK;
+    const uint32_t tiles = (v.n + TILE_THREADS - 1) / TILE_THREADS;
+    if (compact) denied_count_kernel<true><<<tiles, TILE_THREADS, 0, st>>>(v.req0, v.res0, v.n, h->denied);
+    else denied_count_kernel<false><<<tiles, TILE_THREADS, 0, st>>>(v.req0, v.res0, v.n, h->denied);
+    h->launches++;
+    CK(cudaGetLastError());
+    return GCRA_OK;
+}
+
 static bool use_index_path(const gcra_engine *h, uint32_t n) {
     // (the batch counters hold at most 2 x tiles per entry in 16 bits: batches of 2^22 rows and more take the sort pipeline)
     return h->index_min != 0 && n >= h->index_min && n < (1u << 22);
@@ -789,6 +803,7 @@ static int launch_batch(gcra_engine *h, uint32_t n, const void *d_req, bool comp
             sc.mid_recorded = false;
         }
     }
+    RC(enqueue_denied(h, single_view(d_req, d_res, n), compact, st));
     CK(cudaEventRecord(sc.ev_back, st));
     sc.back_recorded = true;
     h->pend_set = -1;          // everything of this batch is ordered on `st`: the next batch waits for all of it
@@ -864,6 +879,7 @@ static int launch_pipelined_view(gcra_engine *h, const BatchView &v, uint32_t n_
         cudaStream_t ts = h->tail_stream;
         CK(cudaStreamWaitEvent(ts, sc.ev_mid, 0));
         RC(enqueue_tail_index(h, sc, v, compact, now_batch, ts, false));
+        RC(enqueue_denied(h, v, compact, ts));
         CK(cudaEventRecord(sc.ev_back, ts));
         sc.back_recorded = true;
         h->pend_set = (int)kn;
@@ -871,6 +887,7 @@ static int launch_pipelined_view(gcra_engine *h, const BatchView &v, uint32_t n_
         return snapshot_async(h, n_rows, ts);
     }
     RC(enqueue_back_sorted(h, sc, v, sorted, ms, false));
+    RC(enqueue_denied(h, v, compact, ms));
     sc.mid_recorded = false;   // (no residue count from this batch)
     CK(cudaEventRecord(sc.ev_back, ms));
     sc.back_recorded = true;
@@ -906,6 +923,7 @@ static void preload_kernels() {
     preload(route_count_kernel); preload(route_scan_kernel); preload(route_scatter_kernel); preload(route_unpermute_kernel);
     preload(p2p_scan_kernel); preload(p2p_scatter_kernel); preload(p2p_signal_req_kernel); preload(p2p_signal_res_kernel);
     preload(p2p_wait_kernel); preload(p2p_unpermute_kernel);
+    preload(denied_count_kernel<false>); preload(denied_count_kernel<true>);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1085,6 +1103,7 @@ void gcra_destroy(gcra_engine *h) {
         cudaFreeHost(sc.h_nres);
         cudaEventDestroy(sc.ev_front); cudaEventDestroy(sc.ev_mid); cudaEventDestroy(sc.ev_back); cudaEventDestroy(sc.ev_fork); cudaEventDestroy(sc.ev_join); cudaEventDestroy(sc.ev_join2);
     }
+    cudaFree(h->denied.keys); cudaFree(h->denied.counts); cudaFree(h->denied.dropped);
     cudaFree(h->d_req); cudaFree(h->d_res); cudaFree(h->route_counts); cudaFree(h->d_pol); cudaFree(h->d_op);
     cudaFreeHost(h->h_op); cudaFreeHost(h->h_counters); cudaFreeHost(h->h_snap);
     for (int i = 0; i < gcra_engine::N_SNAP; i++) cudaEventDestroy(h->ev_snap[i]);
@@ -1450,6 +1469,61 @@ int32_t gcra_peek(gcra_engine *h, uint64_t key_hash, int64_t *tat, int64_t *expi
     if (rc) return rc;
     *found = (uint8_t)h->h_op[0].flag;
     if (*found) { *tat = h->h_op[0].value; *expiry_ns = h->h_op[1].value; }
+    return GCRA_OK;
+}
+
+// ---- metrics bridge: top denied keys (throttlecrab-server/src/metrics.rs:24-64,162-173) --------------------------
+int32_t gcra_track_denied(gcra_engine *h, uint32_t max_keys) {
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    cudaFree(h->denied.keys); cudaFree(h->denied.counts); cudaFree(h->denied.dropped);
+    h->denied = DeniedTable{};
+    h->denied_max = max_keys;
+    h->denied_cap = 0;
+    if (!max_keys) return GCRA_OK;
+    h->denied_cap = 1u << ceil_log2(std::max<uint64_t>(16ULL * max_keys, 1024));
+    CK(cudaMalloc(&h->denied.keys, (size_t)h->denied_cap * sizeof(u64)));
+    CK(cudaMalloc(&h->denied.counts, (size_t)h->denied_cap * sizeof(u64)));
+    CK(cudaMalloc(&h->denied.dropped, sizeof(u64)));
+    CK(cudaMemset(h->denied.keys, 0, (size_t)h->denied_cap * sizeof(u64)));
+    CK(cudaMemset(h->denied.counts, 0, (size_t)h->denied_cap * sizeof(u64)));
+    CK(cudaMemset(h->denied.dropped, 0, sizeof(u64)));
+    h->denied.mask = h->denied_cap - 1;
+    return GCRA_OK;
+}
+
+// the k most denied keys (hash, count), most denied first; *dropped = denials of keys that found the table full.
+// Like the reference's cleanup (metrics.rs:52-64) the table is pruned to its `max_keys` top entries when more than
+// three times as many have accumulated.
+int32_t gcra_top_denied(gcra_engine *h, uint32_t k, uint64_t *key_hashes, uint64_t *counts, uint32_t *n_out, uint64_t *dropped) {
+    CK(cudaSetDevice(h->device));
+    if (n_out) *n_out = 0;
+    if (!h->denied_max) { h->err = "gcra_track_denied first"; return GCRA_INTERNAL; }
+    for (auto &o : h->scr) if (o.back_recorded) CK(cudaEventSynchronize(o.ev_back));
+    std::vector<u64> keys(h->denied_cap), cnts(h->denied_cap);
+    CK(cudaMemcpy(keys.data(), h->denied.keys, keys.size() * sizeof(u64), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(cnts.data(), h->denied.counts, cnts.size() * sizeof(u64), cudaMemcpyDeviceToHost));
+    if (dropped) CK(cudaMemcpy(dropped, h->denied.dropped, sizeof(u64), cudaMemcpyDeviceToHost));
+    std::vector<std::pair<u64, u64>> top;      // (count, key)
+    for (uint32_t i = 0; i < h->denied_cap; i++) if (keys[i]) top.emplace_back(cnts[i], keys[i]);
+    std::sort(top.begin(), top.end(), [](const std::pair<u64, u64> &a, const std::pair<u64, u64> &b) {
+        return a.first != b.first ? a.first > b.first : a.second < b.second;
+    });
+    const uint32_t n = (uint32_t)std::min<size_t>(k, top.size());
+    for (uint32_t i = 0; i < n; i++) { key_hashes[i] = top[i].second; counts[i] = top[i].first; }
+    if (n_out) *n_out = n;
+    if (top.size() > (size_t)3 * h->denied_max) {
+        std::fill(keys.begin(), keys.end(), 0);
+        std::fill(cnts.begin(), cnts.end(), 0);
+        for (uint32_t i = 0; i < h->denied_max; i++) {
+            uint32_t s = (uint32_t)(mix64(top[i].second ^ 0x9E3779B97F4A7C15ULL)) & h->denied.mask;
+            while (keys[s]) s = (s + 1) & h->denied.mask;
+            keys[s] = top[i].second;
+            cnts[s] = top[i].first;
+        }
+        CK(cudaMemcpy(h->denied.keys, keys.data(), keys.size() * sizeof(u64), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->denied.counts, cnts.data(), cnts.size() * sizeof(u64), cudaMemcpyHostToDevice));
+    }
     return GCRA_OK;
 }
 

@@ -1262,4 +1262,61 @@ route_unpermute_kernel(const gcra_result *__restrict__ routed, const u32 *__rest
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// metrics bridge: denied requests per key, from the kernels' own outputs
+// ---------------------------------------------------------------------------------------------
+// The reference counts denials per key string in a HashMap and keeps the top N (throttlecrab-server/src/
+// metrics.rs:24-64,162-173).  Here a pass over a finished batch (request rows + result rows) counts the denied rows
+// per key hash: every 256-row tile aggregates in a shared-memory hash set, then adds each distinct key's count to an
+// open-addressed table in HBM -- a key already in the table costs a load and a posted add, only a new key a CAS.
+// A full table drops new keys (counted); gcra_top_denied prunes it to the top entries like the reference's cleanup.
+struct DeniedTable {
+    u64 *keys;      // 0 = empty
+    u64 *counts;
+    u32 mask;       // capacity - 1
+    u64 *dropped;
+};
+constexpr u32 DENIED_HASH = 512;
+
+template <bool COMPACT>
+__global__ void __launch_bounds__(TILE_THREADS)
+denied_count_kernel(const unsigned char *__restrict__ req, const gcra_result *__restrict__ res, u32 n, DeniedTable t) {
+    constexpr u32 RSZ = COMPACT ? sizeof(gcra_request16) : sizeof(gcra_request);
+    __shared__ u64 hkey[DENIED_HASH];
+    __shared__ u32 hcnt[DENIED_HASH];
+    for (u32 i = threadIdx.x; i < DENIED_HASH; i += TILE_THREADS) { hkey[i] = 0; hcnt[i] = 0; }
+    __syncthreads();
+    const u32 i = blockIdx.x * TILE_THREADS + threadIdx.x;
+    if (i < n) {
+        const longlong2 tail = reinterpret_cast<const longlong2 *>(res + i)[1];      // retry_after, status | allowed << 32
+        const bool denied = (u32)tail.y == GCRA_OK && ((tail.y >> 32) & 0xff) == 0;
+        if (denied) {
+            u64 k = *reinterpret_cast<const u64 *>(req + (size_t)i * RSZ);
+            if (k == 0) k = 1;                                                          // 0 marks an empty entry
+            u32 h = (u32)(mix64(k) >> 55);                                              // 9 bits
+            for (;;) {
+                const u64 old = atomicCAS(&hkey[h], 0ULL, k);
+                if (old == 0 || old == k) { atomicAdd(&hcnt[h], 1u); break; }
+                h = (h + 1) & (DENIED_HASH - 1);
+            }
+        }
+    }
+    __syncthreads();
+    for (u32 e = threadIdx.x; e < DENIED_HASH; e += TILE_THREADS) {
+        const u64 k = hkey[e];
+        if (k == 0) continue;
+        u32 h = (u32)(mix64(k ^ 0x9E3779B97F4A7C15ULL)) & t.mask;
+        bool done = false;
+        for (u32 probe = 0; probe < 64 && !done; probe++) {
+            u64 cur = t.keys[h];                                    // (a stale L1 line shows "empty": then the CAS decides)
+            if (cur == 0) cur = atomicCAS(&t.keys[h], 0ULL, k) == 0 ? k : t.keys[h];
+            if (cur == 0) cur = __ldcg(&t.keys[h]);
+            if (cur == k) { atomicAdd(&t.counts[h], (u64)hcnt[e]); done = true; }
+            else h = (h + 1) & t.mask;
+        }
+        if (!done) atomicAdd(t.dropped, (u64)hcnt[e]);
+    }
+}
+
 }  // namespace gcra
