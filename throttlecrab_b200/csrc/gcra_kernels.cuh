@@ -1310,8 +1310,7 @@ denied_count_kernel(const unsigned char *__restrict__ req, const gcra_result *__
         bool done = false;
         for (u32 probe = 0; probe < 64 && !done; probe++) {
             u64 cur = t.keys[h];                                    // (a stale L1 line shows "empty": then the CAS decides)
-            if (cur == 0) cur = atomicCAS(&t.keys[h], 0ULL, k) == 0 ? k : t.keys[h];
-            if (cur == 0) cur = __ldcg(&t.keys[h]);
+            if (cur == 0) { const u64 old = atomicCAS(&t.keys[h], 0ULL, k); cur = old == 0 ? k : old; }
             if (cur == k) { atomicAdd(&t.counts[h], (u64)hcnt[e]); done = true; }
             else h = (h + 1) & t.mask;
         }
