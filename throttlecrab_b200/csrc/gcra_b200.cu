@@ -506,6 +506,7 @@ static int apply_policy(gcra_engine *h, int64_t now_ns) {
 }
 
 // the cluster kernel: cluster dimension given at launch (cudaLaunchKernelEx)
+template <bool BY_ROW>
 static int launch_giant(gcra_engine *h, Scratch &sc, const u64 *src, const OutMap &om, cudaStream_t st) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((128 / CLUSTER_CTAS) * CLUSTER_CTAS);
@@ -520,9 +521,9 @@ static int launch_giant(gcra_engine *h, Scratch &sc, const u64 *src, const OutMa
     cfg.numAttrs = 1;
     if (CLUSTER_CTAS > 8) {
         static bool once = false;
-        if (!once) { cudaFuncSetAttribute(decide_runs_kernel<CLUSTER_CTAS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); once = true; }
+        if (!once) { cudaFuncSetAttribute(decide_runs_kernel<CLUSTER_CTAS, BY_ROW>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); once = true; }
     }
-    CK(cudaLaunchKernelEx(&cfg, decide_runs_kernel<CLUSTER_CTAS>, h->tab, (const u64 *)src, (const Req *)sc.drec, om,
+    CK(cudaLaunchKernelEx(&cfg, decide_runs_kernel<CLUSTER_CTAS, BY_ROW>, h->tab, (const u64 *)src, (const Req *)sc.drec, om,
                           (const LongRun *)sc.giant_runs, (const u32 *)(sc.long_count + 1)));
     return GCRA_OK;
 }
@@ -571,31 +572,38 @@ static int enqueue_sort(gcra_engine *h, Scratch &sc, uint32_t n_max, const u32 *
     return GCRA_OK;
 }
 
-// the warp-cooperative compare-and-update over sorted keys + the hot-run kernels
-static int enqueue_decide_sorted(gcra_engine *h, Scratch &sc, uint32_t n_max, const u32 *n_dev, const u64 *src,
-                                 const OutMap &om, cudaStream_t st) {
+template <bool BY_ROW>
+static int enqueue_decide_sorted_t(gcra_engine *h, Scratch &sc, uint32_t n_max, const u32 *n_dev, const u64 *src,
+                                   const OutMap &om, cudaStream_t st) {
     CK(cudaMemsetAsync(sc.long_count, 0, 2 * sizeof(u32), st));
     const uint32_t warps = (n_max + 31) / 32;
     uint32_t grid = (warps + DECIDE_THREADS / 32 - 1) / (DECIDE_THREADS / 32);
     if (n_dev) grid = std::min<uint32_t>(grid, 4 * 148);
-    decide_kernel<<<grid, DECIDE_THREADS, 0, st>>>(h->tab, src, sc.drec, n_max, n_dev, om, sc.long_runs, sc.giant_runs,
-                                                   sc.long_count, 0);
+    decide_kernel<BY_ROW><<<grid, DECIDE_THREADS, 0, st>>>(h->tab, src, sc.drec, n_max, n_dev, om, sc.long_runs, sc.giant_runs,
+                                                           sc.long_count, 0);
     h->launches++;
     if (n_max >= GIANT_RUN_MIN) {
         // the two hot-run kernels work on disjoint runs: the one-CTA-per-run kernel goes to a side
         // stream and overlaps the cluster kernel (fork/join with events)
         CK(cudaEventRecord(sc.ev_fork, st));
         CK(cudaStreamWaitEvent(h->aux_stream, sc.ev_fork, 0));
-        decide_runs_kernel<1><<<148, LONG_THREADS, 0, h->aux_stream>>>(h->tab, src, sc.drec, om, sc.long_runs, sc.long_count);
+        decide_runs_kernel<1, BY_ROW><<<148, LONG_THREADS, 0, h->aux_stream>>>(h->tab, src, sc.drec, om, sc.long_runs, sc.long_count);
         CK(cudaEventRecord(sc.ev_join, h->aux_stream));
-        RC(launch_giant(h, sc, src, om, st));   // hottest keys: one cluster per run
+        RC(launch_giant<BY_ROW>(h, sc, src, om, st));   // hottest keys: one cluster per run
         CK(cudaStreamWaitEvent(st, sc.ev_join, 0));
         h->launches += 2;
     } else if (n_max >= LONG_RUN_MIN) {
-        decide_runs_kernel<1><<<148, LONG_THREADS, 0, st>>>(h->tab, src, sc.drec, om, sc.long_runs, sc.long_count);
+        decide_runs_kernel<1, BY_ROW><<<148, LONG_THREADS, 0, st>>>(h->tab, src, sc.drec, om, sc.long_runs, sc.long_count);
         h->launches++;
     }
     return GCRA_OK;
+}
+
+// the warp-cooperative compare-and-update over sorted keys + the hot-run kernels
+static int enqueue_decide_sorted(gcra_engine *h, Scratch &sc, uint32_t n_max, const u32 *n_dev, const u64 *src,
+                                 const OutMap &om, cudaStream_t st) {
+    return om.by_row ? enqueue_decide_sorted_t<true>(h, sc, n_max, n_dev, src, om, st)
+                     : enqueue_decide_sorted_t<false>(h, sc, n_max, n_dev, src, om, st);
 }
 
 // per-set buffers of the index-order pipeline for batches of up to `rows` row ids
@@ -915,7 +923,9 @@ static void preload_kernels() {
     preload(ingest_kernel<false>); preload(ingest_kernel<true>);
     preload(small_batch_kernel<false>); preload(small_batch_kernel<true>);
     preload(sort_hist_kernel); preload(sort_rowscan_kernel); preload(sort_scatter_kernel); preload(sort_pass_fused_kernel);
-    preload(decide_kernel); preload(decide_runs_kernel<1>); preload(decide_runs_kernel<CLUSTER_CTAS>);
+    preload(decide_kernel<false>); preload(decide_kernel<true>);
+    preload(decide_runs_kernel<1, false>); preload(decide_runs_kernel<CLUSTER_CTAS, false>);
+    preload(decide_runs_kernel<1, true>); preload(decide_runs_kernel<CLUSTER_CTAS, true>);
     preload(probe_kernel<false>); preload(probe_kernel<true>);
     preload(decide_index_kernel<false>); preload(decide_index_kernel<true>);
     preload(resolve_kernel<false>); preload(resolve_kernel<true>);

@@ -405,7 +405,8 @@ struct OutMap {
     const PolicyDerived *pol;
     u32 npol;
     i64 now_batch;
-    __device__ __forceinline__ gcra_result *at(u32 i) const { return by_row ? view.res_at(i) : out + i; }
+    template <bool BY_ROW>
+    __device__ __forceinline__ gcra_result *at(u32 i) const { return BY_ROW ? view.res_at(i) : out + i; }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -478,8 +479,9 @@ constexpr int LONG_THREADS = 512;
 constexpr int CLUSTER_CTAS = GCRA_CLUSTER;
 struct LongRun { u32 start, len; };
 
+template <bool BY_ROW>
 __device__ __forceinline__ void load_req(const Req *__restrict__ drec, const OutMap &om, u32 idx, Req &r) {
-    if (om.by_row) {
+    if (BY_ROW) {
         // (rows in the residue passed validation in pass A: the status is 0)
         u64 key_hash;
         if (om.compact) parse_request<true>(om.view.req_at(idx, sizeof(gcra_request16)), om.pol, om.npol, om.now_batch, key_hash, r);
@@ -526,7 +528,9 @@ __device__ __forceinline__ void store_state(const Table &t, u32 slot, const RunS
 #endif
 constexpr int DECIDE_THREADS = GCRA_DECIDE_THREADS;   // warps are independent: the CTA size only sets scheduling granularity
 
-// one warp, one chunk of 32 sorted positions (see the comment above run_chunk)
+// one warp, one chunk of 32 sorted positions (see the comment above run_chunk); BY_ROW: the sorted payload is a row
+// id of the batch (residue of the index-order pipeline), else a batch index into drec / out
+template <bool BY_ROW>
 __device__ __forceinline__ void decide_chunk(const Table &t, const u64 *sorted, const Req *__restrict__ drec, u32 n,
                                              const OutMap &out, LongRun *__restrict__ long_runs,
                                              LongRun *__restrict__ giant_runs, u32 *__restrict__ long_count,
@@ -590,7 +594,7 @@ __device__ __forceinline__ void decide_chunk(const Table &t, const u64 *sorted, 
 
     Req r = {0, 0, 0, 0};
     const u32 idx = (u32)e;
-    if (mine) load_req(drec, out, idx, r);
+    if (mine) load_req<BY_ROW>(drec, out, idx, r);
     // run heads read the entry; the run's lanes get it by shuffle
     RunState s = {0, EXP_EMPTY, 0};
     if (head && mine) load_state(t, slot, s);
@@ -606,7 +610,7 @@ __device__ __forceinline__ void decide_chunk(const Table &t, const u64 *sorted, 
     u32 n_allowed = 0, n_denied = 0;
     if (mine) {
         Outputs o = outputs_of(fin, r);
-        write_result(out.at(idx), o.remaining, o.reset_after, o.retry_after, 0, fin.allowed ? 1 : 0);
+        write_result(out.template at<BY_ROW>(idx), o.remaining, o.reset_after, o.retry_after, 0, fin.allowed ? 1 : 0);
         n_allowed += fin.allowed ? 1 : 0;
         n_denied += fin.allowed ? 0 : 1;
     }
@@ -638,7 +642,7 @@ __device__ __forceinline__ void decide_chunk(const Table &t, const u64 *sorted, 
         u64 e2 = b2 + lane < n ? sorted[b2 + lane] : ~0ULL;
         bool in_run = (u32)(e2 >> 32) == slot31 && b2 + lane < n;
         Req r2 = {0, 0, 0, 0};
-        if (in_run) load_req(drec, out, (u32)e2, r2);
+        if (in_run) load_req<BY_ROW>(drec, out, (u32)e2, r2);
         for (;;) {
             const u32 rm = __ballot_sync(0xffffffffu, in_run);   // a prefix (sorted)
             if (rm == 0) break;
@@ -650,7 +654,7 @@ __device__ __forceinline__ void decide_chunk(const Table &t, const u64 *sorted, 
             if (rm == 0xffffffffu) {
                 e3 = b3 + lane < n ? sorted[b3 + lane] : ~0ULL;
                 in3 = (u32)(e3 >> 32) == slot31 && b3 + lane < n;
-                if (in3) load_req(drec, out, (u32)e3, r3);
+                if (in3) load_req<BY_ROW>(drec, out, (u32)e3, r3);
             }
             RunState s2 = cs;
             Decision f2;
@@ -658,7 +662,7 @@ __device__ __forceinline__ void decide_chunk(const Table &t, const u64 *sorted, 
             run_chunk(lane, in_run, rm, r2, s2, f2, ch2, exp_hits);
             if (in_run) {
                 Outputs o = outputs_of(f2, r2);
-                write_result(out.at((u32)e2), o.remaining, o.reset_after, o.retry_after, 0, f2.allowed ? 1 : 0);
+                write_result(out.template at<BY_ROW>((u32)e2), o.remaining, o.reset_after, o.retry_after, 0, f2.allowed ? 1 : 0);
                 n_allowed += f2.allowed ? 1 : 0;
                 n_denied += f2.allowed ? 0 : 1;
             }
@@ -692,6 +696,7 @@ __device__ __forceinline__ void decide_chunk(const Table &t, const u64 *sorted, 
 #ifndef GCRA_DECIDE_MINBLOCKS
 #define GCRA_DECIDE_MINBLOCKS (1024 / GCRA_DECIDE_THREADS)
 #endif
+template <bool BY_ROW>
 __global__ void __launch_bounds__(DECIDE_THREADS, GCRA_DECIDE_MINBLOCKS)
 decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ drec, u32 n_host,
               const u32 *__restrict__ n_dev, OutMap out, LongRun *__restrict__ long_runs,
@@ -699,7 +704,7 @@ decide_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ d
     const u32 n = sort_count(n_host, n_dev);
     const u32 warps_total = gridDim.x * (DECIDE_THREADS / 32);
     for (u32 wg = (blockIdx.x * DECIDE_THREADS + threadIdx.x) >> 5; wg * 32 < n; wg += warps_total)
-        decide_chunk(t, sorted, drec, n, out, long_runs, giant_runs, long_count, wg, threadIdx.x & 31, mode);
+        decide_chunk<BY_ROW>(t, sorted, drec, n, out, long_runs, giant_runs, long_count, wg, threadIdx.x & 31, mode);
 }
 
 // Small batches (n < LONG_RUN_MIN, e.g. one RateLimiter::rate_limit call or a lightly loaded actor): ONE CTA
@@ -736,7 +741,7 @@ small_batch_kernel(Table t, const void *__restrict__ req_base, const PolicyDeriv
     OutMap om;
     om.out = out;
     om.by_row = 0;
-    decide_chunk(t, keys, drec, n, om, nullptr, nullptr, nullptr, tid >> 5, tid & 31);
+    decide_chunk<false>(t, keys, drec, n, om, nullptr, nullptr, nullptr, tid >> 5, tid & 31);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -793,7 +798,7 @@ struct Cands {
 
 struct PubState { i64 tat, exp; };
 
-template <int CTAS>
+template <int CTAS, bool BY_ROW>
 __global__ void __launch_bounds__(LONG_THREADS, 1)
 decide_runs_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restrict__ drec,
                    OutMap out, const LongRun *__restrict__ runs,
@@ -832,13 +837,13 @@ decide_runs_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restric
         bool active = gpos < len;
         u32 idx = 0;
         Req r = {0, 0, 0, 0};
-        if (active) { idx = (u32)sorted[start + gpos]; load_req(drec, out, idx, r); }
+        if (active) { idx = (u32)sorted[start + gpos]; load_req<BY_ROW>(drec, out, idx, r); }
         for (u32 off = 0; off < len; off += STRIDE) {
             const u32 noff = off + STRIDE;
             const bool nactive = noff + gpos < len;
             u32 nidx = 0;
             Req nr = {0, 0, 0, 0};
-            if (nactive) { nidx = (u32)sorted[start + noff + gpos]; load_req(drec, out, nidx, nr); }
+            if (nactive) { nidx = (u32)sorted[start + noff + gpos]; load_req<BY_ROW>(drec, out, nidx, nr); }
             bool pending = active;
             for (;;) {
                 const bool fsm = n_changes >= FSM_AFTER;
@@ -930,7 +935,7 @@ decide_runs_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restric
                     cd.get(in_idx, ct, ce);
                     const Decision d = decide(ct, ce, r);
                     const Outputs o = outputs_of(d, r);
-                    write_result(out.at(idx), o.remaining, o.reset_after, o.retry_after, 0, d.allowed ? 1 : 0);
+                    write_result(out.template at<BY_ROW>(idx), o.remaining, o.reset_after, o.retry_after, 0, d.allowed ? 1 : 0);
                     n_allowed += d.allowed ? 1 : 0;
                     n_denied += d.allowed ? 0 : 1;
                     if (d.allowed && !d.live && ce >= 0) exp_hits++;
@@ -969,7 +974,7 @@ decide_runs_kernel(Table t, const u64 *__restrict__ sorted, const Req *__restric
             cd.get(cur, fs.tat, fs.exp);
             if (fs.tat != s0.tat || fs.exp != s0.exp) {
                 Req first;
-                load_req(drec, out, (u32)sorted[start], first);
+                load_req<BY_ROW>(drec, out, (u32)sorted[start], first);
                 fs.ei = first.ei;
                 store_state(t, slot, fs, was_phantom);
                 if (was_phantom) real_inc++;
