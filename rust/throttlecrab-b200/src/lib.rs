@@ -6,7 +6,7 @@ use std::time::{Duration, SystemTime, UNIX_EPOCH};
 use throttlecrab::{CellError, RateLimitResult, Store};
 
 #[repr(C)] pub struct GcraConfig { capacity: u64, device: i32, store_kind: i32, p0: u64, p1: u64, p2: u64,
-                                   created_ns: i64, max_batch: u32, flags: u32 }
+                                   created_ns: i64, max_batch: u32, flags: u32, hash_seed: [u64; 2] }
 #[repr(C)] #[derive(Clone, Copy)] pub struct GcraRequest { pub key_hash: u64, pub max_burst: i64,
     pub count_per_period: i64, pub period: i64, pub quantity: i64, pub now_ns: i64 }
 #[repr(C)] #[derive(Clone, Copy, Default)] pub struct GcraResult { pub remaining: i64, pub reset_after_ns: i64,
@@ -37,7 +37,8 @@ impl GpuStore {
     pub fn periodic(capacity: usize) -> Result<Self, String> { Self::new(capacity, 0) }
     fn new(capacity: usize, kind: i32) -> Result<Self, String> {
         let cfg = GcraConfig { capacity: capacity as u64, device: 0, store_kind: kind, p0: 0, p1: 0, p2: 0,
-                               created_ns: ns(SystemTime::now()), max_batch: 0, flags: 0 };
+                               created_ns: ns(SystemTime::now()), max_batch: 0, flags: 8 /* GCRA_FLAG_RANDOM_SEED */,
+                               hash_seed: [0, 0] };
         let mut h = std::ptr::null_mut();
         if unsafe { gcra_create(&cfg, &mut h) } != 0 { return Err("gcra_create failed (no CUDA device)".into()); }
         Ok(GpuStore { h })
