@@ -638,8 +638,11 @@ static int enqueue_denied(gcra_engine *h, const BatchView &v, bool compact, cuda
 }
 
 static bool use_index_path(const gcra_engine *h, uint32_t n) {
-    // (the batch counters hold at most 2 x tiles per entry in 16 bits: batches of 2^22 rows and more take the sort pipeline)
-    return h->index_min != 0 && n >= h->index_min && n < (1u << 22);
+    // The batch counters are 16-bit fields that receive at most 2 per distinct slot and 256-row tile.  Slots that
+    // share a hashed entry add up: k slots that occur in EVERY tile reach 2 k x tiles.  Up to 2^21 rows (8192 tiles)
+    // that stays below 65536 unless four such ultra-hot keys (each > 0.4 % of the traffic) hash to one of the 2^23+
+    // entries; larger batches take the sort pipeline.
+    return h->index_min != 0 && n >= h->index_min && n <= (1u << 21);
 }
 
 static uint32_t view_max_rows(const BatchView &v) { return v.nseg == 1 ? v.n : (v.nseg << v.cap_shift); }

@@ -88,7 +88,8 @@ __device__ __forceinline__ void stage_tile(unsigned char *stage, u64 *bar, const
 //             finds the distinct slots of every 256-row tile with a hash set in shared memory and adds
 //             min(count in the tile, 2) per distinct slot with ONE posted RED (no global atomic ever returns a
 //             value: returning atomics are throttled by the few that an SM can keep in flight).  >= 2 <=> shared.
-//             At most 2 x (number of tiles) per entry: the host keeps batches below 2^22 rows on this pipeline.
+//             At most 2 x (number of tiles) per slot: the host keeps batches of more than 2^21 rows off this
+//             pipeline, so even several ultra-hot slots sharing one entry stay far below 65536.
 //   pend      1 bit per entry, written by the PREVIOUS batch's pass C: a slot of the entry still has residue
 //             requests in that batch's sorted tail, which may run concurrently with this batch's passes B and C;
 //             this batch's requests on such a slot are deferred to its own tail (tails run one after another)
