@@ -575,7 +575,8 @@ static int enqueue_sort(gcra_engine *h, Scratch &sc, uint32_t n_max, const u32 *
 template <bool BY_ROW>
 static int enqueue_decide_sorted_t(gcra_engine *h, Scratch &sc, uint32_t n_max, const u32 *n_dev, const u64 *src,
                                    const OutMap &om, cudaStream_t st) {
-    CK(cudaMemsetAsync(sc.long_count, 0, 2 * sizeof(u32), st));
+    // (sort pipeline: the work-list counters were cleared at the end of the front half, off this stream)
+    if (BY_ROW) CK(cudaMemsetAsync(sc.long_count, 0, 2 * sizeof(u32), st));
     const uint32_t warps = (n_max + 31) / 32;
     uint32_t grid = (warps + DECIDE_THREADS / 32 - 1) / (DECIDE_THREADS / 32);
     if (n_dev) grid = std::min<uint32_t>(grid, 4 * 148);
@@ -684,6 +685,7 @@ static int enqueue_front(gcra_engine *h, Scratch &sc, const BatchView &v, bool i
     if (timed) CK(cudaEventRecord(h->ev[1], st));
     RC(enqueue_sort(h, sc, n, nullptr, st, sorted_out));
     if (timed) CK(cudaEventRecord(h->ev[2], st));
+    CK(cudaMemsetAsync(sc.long_count, 0, 2 * sizeof(u32), st));   // hot-run work lists of this batch's decide kernels
     return GCRA_OK;
 }
 
