@@ -222,7 +222,7 @@ int32_t gcra_sync(gcra_engine *h);
  * the launching stream: [0] total, [1] ingest (hash probe), [2] sort, [3] decide */
 int32_t gcra_last_kernel_ms(gcra_engine *h, float out[4]);
 /* the most recent batch that took the index-order pipeline on ONE stream (gcra_rate_limit_batch_device): device
- * time (ms) of [0] probe, [1] note, [2] decide in batch order, [3] resolve, [4] bitmap clear + residue-count copy,
+ * time (ms) of [0] probe, [1] unused (0), [2] decide in batch order, [3] resolve, [4] bitmap clear + residue-count copy,
  * [5] residue radix sort, [6] residue decide + hot-run kernels */
 int32_t gcra_last_kernel_ms_detail(gcra_engine *h, float out[7]);
 /* timing experiments only (tools/): a non-zero mask makes pass B of the index-order pipeline skip parts of its work

@@ -272,7 +272,7 @@ class _GpuStore:
     def last_kernel_ms_detail(self):
         out = (C.c_float * 7)()
         self._check(self._L.gcra_last_kernel_ms_detail(self._h, C.byref(out)))
-        return dict(zip(("probe", "note", "decide_index", "resolve", "clear", "residue_sort", "residue_decide"),
+        return dict(zip(("probe", "unused", "decide_index", "resolve", "clear", "residue_sort", "residue_decide"),
                         [float(x) for x in out]))
 
     def last_sweep_ms(self):

@@ -708,6 +708,7 @@ static int enqueue_mid_index(gcra_engine *h, Scratch &sc, Scratch &next, const B
     if (compact) {
         decide_index_kernel<true><<<grid, TILE_THREADS, 0, st>>>(h->tab, v, h->d_pol, h->npol, now_batch, sc.slot_arr,
                                                                  sc.bitmap, sc.pend, h->bm_mask, sc.flags, h->epoch, hp, h->dbg);
+        if (timed) CK(cudaEventRecord(h->evd[3], st));
         resolve_kernel<true><<<rgrid, TILE_THREADS, 0, st>>>(h->tab, v, h->d_pol, h->npol, now_batch, sc.slot_arr,
                                                              h->bm_mask, sc.flags, h->epoch, ctrl, status, sc.keys_a,
                                                              next.pend, sc.h_nres, h->max_batch);
