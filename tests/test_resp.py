@@ -280,3 +280,91 @@ def test_native_pipeline_through_the_pinned_ring():
     want = process_pipeline(buf, a.rate_limit_batch, NOW)
     got = process_pipeline_native(buf, b, NOW, ring=ring, slot=1)
     assert got == want and got[2] == 2999
+
+
+def _raw_throttle(key_bytes, *nums):
+    parts = [b"THROTTLE", key_bytes] + [str(x).encode() for x in nums]
+    return b"*%d\r\n" % len(parts) + b"".join(b"$%d\r\n%s\r\n" % (len(p), p) for p in parts)
+
+
+def test_native_batch_parser_rejects_what_from_utf8_rejects():
+    """resp.rs:110 turns every bulk string into a String: a key that is not well-formed UTF-8 fails the frame.  The
+    fast path hands exactly those frames to the general parser (stop 2) and accepts every well-formed key."""
+    import ctypes as C
+    from throttlecrab_b200 import _native
+    L = _native.lib()
+    req = np.zeros(4, tc.REQ_DTYPE)
+
+    def accepted(key):
+        buf = _raw_throttle(key, 3, 100, 60)
+        used, cnt, stop = C.c_uint64(), C.c_uint32(), C.c_int32()
+        assert L.gcra_resp_parse_throttle(None, buf, len(buf), NOW, 4, req.ctypes.data, C.byref(used), C.byref(cnt),
+                                          C.byref(stop)) == 0
+        assert (cnt.value, stop.value) in ((1, 0), (0, 2))
+        return cnt.value == 1
+    rng = np.random.default_rng(11)
+    cases = [b"", b"plain", "kéy".encode(), "€".encode(), "\U0001f980".encode(), b"\xc0\x80", b"\xc1\xbf",
+             b"\xe0\x80\x80", b"\xe0\x9f\xbf", b"\xe0\xa0\x80", b"\xed\x9f\xbf", b"\xed\xa0\x80", b"\xef\xbf\xbf",
+             b"\xf0\x8f\xbf\xbf", b"\xf0\x90\x80\x80", b"\xf4\x8f\xbf\xbf", b"\xf4\x90\x80\x80", b"\xf5\x80\x80\x80",
+             b"\x80", b"\xbf", b"ab\xc3", b"ab\xe2\x82", b"\xf0\x9f\xa6", b"\xff", b"a\xc3\xa9b\xe2\x82\xacc"]
+    for _ in range(3000):
+        n = int(rng.integers(1, 6))
+        cases.append(bytes(rng.choice([0x41, 0x7f, 0x80, 0x9f, 0xa0, 0xbf, 0xc1, 0xc2, 0xdf, 0xe0, 0xe1, 0xec, 0xed,
+                                       0xee, 0xef, 0xf0, 0xf1, 0xf3, 0xf4, 0xf5, 0x8f, 0x90], n).astype(np.uint8)))
+    for key in cases:
+        try:
+            key.decode("utf-8")
+            ok = True
+        except UnicodeDecodeError:
+            ok = False
+        assert accepted(key) == ok, key
+    # and the pipeline as a whole answers such a frame like the general path (a parse error closes the connection)
+    from throttlecrab_b200.resp import process_pipeline_native
+    buf = _raw_throttle(b"good", 3, 100, 60) + _raw_throttle(b"bad\xff", 3, 100, 60) + _raw_throttle(b"after", 3, 100, 60)
+    assert process_pipeline_native(buf, _FakeLimiter(), NOW) == process_pipeline(buf, OracleEngine(), NOW)
+
+
+def test_native_pipeline_fuzz_against_the_general_pipeline():
+    """Seeded fuzz: pipelines of well-formed frames, frames with flipped/dropped/inserted bytes and raw garbage, cut
+    at a random byte; the native fast path + fallback must answer byte for byte like the general pipeline (replies,
+    bytes consumed, commands applied, close reason)."""
+    from throttlecrab_b200.resp import process_pipeline_native
+    rng = np.random.default_rng(20260923)
+    keys = [b"a", b"user:1", "kéy".encode(), b"", b"x" * 70, b"\xff\xfe", b"with\r\ncrlf", b"-1", b"*5", b"$3"]
+    nums = [0, 1, 2, 3, 5, 60, 100, -1, -5, 2**31, 2**63 - 1, -2**63, 2**63, "abc", "", "+7", "007", " 5", "5 ", "1e3"]
+
+    def frame():
+        kind = int(rng.integers(0, 10))
+        if kind <= 5:
+            args = [nums[int(rng.integers(0, len(nums)))] if rng.random() < 0.15 else int(rng.integers(1, 200))
+                    for _ in range(int(rng.choice([3, 3, 3, 4, 4, 2, 5])))]
+            f = _raw_throttle(keys[int(rng.integers(0, len(keys)))], *args)
+            if rng.random() < 0.1:
+                f = f.replace(b"THROTTLE", rng.choice([b"throttle", b"Throttle", b"THROTTLF", b"THROTTL"]).item(), 1)
+            return f
+        if kind == 6:
+            return _cmd(*[["PING"], ["PING", "hello"], ["QUIT"], ["UNKNOWN"], ["throttle", "k", 3, 100, 60],
+                          ["THROTTLE", "k", 3, 100, 60, 2]][int(rng.integers(0, 6))])
+        if kind == 7:                                               # a damaged throttle frame
+            f = bytearray(_raw_throttle(b"dmg", 3, 100, 60))
+            for _ in range(int(rng.integers(1, 3))):
+                op, pos = int(rng.integers(0, 3)), int(rng.integers(0, len(f)))
+                if op == 0:
+                    f[pos] = int(rng.integers(0, 256))
+                elif op == 1:
+                    del f[pos]
+                else:
+                    f.insert(pos, int(rng.choice([0x0d, 0x0a, 0x24, 0x2a, 0x3a, 0x2d, 0x30, 0x39, 0xff])))
+            return bytes(f)
+        if kind == 8:
+            return [b"+OK\r\n", b":5\r\n", b"$-1\r\n", b"*0\r\n", b"*-1\r\n", b"$5\r\nab\r\n", b"*5\r\n$8\r\nTHROTTLE\r\n$99999999999\r\n",
+                    b"*5\r\n$8\r\nTHROTTLE\r\n$-3\r\n", b"*99999999999\r\n", b"\r\n"][int(rng.integers(0, 10))]
+        return bytes(rng.integers(0, 256, int(rng.integers(1, 12))).astype(np.uint8))
+
+    for case in range(400):
+        buf = b"".join(frame() for _ in range(int(rng.integers(1, 12))))
+        if rng.random() < 0.4 and len(buf) > 1:
+            buf = buf[:int(rng.integers(1, len(buf)))]
+        want = process_pipeline(buf, OracleEngine(), NOW)
+        got = process_pipeline_native(buf, _FakeLimiter(), NOW)
+        assert got == want, (case, buf)
