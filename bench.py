@@ -532,6 +532,15 @@ def main():
             sto.close()
         else:
             parity = sharded_parity(tc, oracle, dist, rank, world, n_keys, n_local_keys, tr, res_all, W, K)
+            # a peer-memory wait that gave up (a rank never delivered a tick) raises a flag in the rank's window
+            try:
+                gave_up = sh.error() if hasattr(sh, "error") else 0
+            except Exception:
+                gave_up = -1
+            flag = torch.tensor([gave_up], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            if parity is not None:
+                parity["peer_wait_gave_up"] = int(flag.item())
 
     # ---------------------------------------------------------------- K2 (N=1)
     sweep = None
